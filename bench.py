@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of BASELINE.json: reduce_by_key on 1e9 synthetic (u64,u64) pairs,
+1e6 distinct keys, sum, 8 map → 8 reduce partitions, on one B200 (configs[1]); N>1 = the same
+per-GPU workload on every rank (weak scaling) with the combined rows exchanged by one all-to-all-v.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: create the shuffle, run the M map tasks
+(map-side combine: hash_agg_kernel), seal (merge + partition the combined rows).  `value` is
+whole-job pairs/s with the input resident in HBM; `e2e` is the same metric through the public API
+(vega_b200.Context.parallelize(...).reduce_by_key(...).collect()) with pinned HOST buffers, the
+H2D copy of the rows and the D2H copy of the result inside the timed region.
+`--impl reference` times the reference's CPU algorithm (oracle port: vega is Rust and cannot be
+built here) on the host cores on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_PAIR = 16.0       # 16 B read per pair (+16 B per distinct key written)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", delete=False, suffix=".csv")
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_port_run(n_rows, D, M, R, threads, steps, warmup):
+    """The reference's CPU algorithm (oracle/vega_oracle.c) on `n_rows` rows of the same generator."""
+    from oracle import oracle as O
+    keys, vals = O.gen_uniform(0, n_rows, D, 1, 2)
+    times = []
+    for i in range(warmup + steps):
+        dt, nk = O.shuffle_timed("sum", keys, vals, M, R, threads=threads)
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=float, default=1e9, help="pairs per GPU")
+    ap.add_argument("--distinct", type=float, default=1e6)
+    ap.add_argument("--maps", type=int, default=8, help="map partitions per GPU")
+    ap.add_argument("--reduces", type=int, default=8, help="reduce partitions per GPU")
+    ap.add_argument("--e2e-rows", type=float, default=None)
+    ap.add_argument("--cpu-rows", type=float, default=5e7)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    n_gpus = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N, D, M, R = int(args.rows), int(args.distinct), args.maps, args.reduces
+    nproc = os.cpu_count() or 1
+    workload = f"reduce_by_key(sum) {N:.0e} (u64,u64) pairs/GPU, {D:.0e} distinct keys, {M} map x {R * max(world, 1)} reduce partitions"
+
+    # ---------------------------------------------------------------- reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n_cpu = int(min(args.cpu_rows, N))
+        threads = min(M, nproc)
+        times = cpu_port_run(n_cpu, D, M, R, threads, args.steps, args.warmup)
+        tot = sum(times)
+        val = n_cpu * len(times) / tot
+        line = {
+            "impl": "reference", "metric": "reduce_by_key (K,V) pairs/sec", "value": val, "unit": "pairs/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload, "sample": f"each step = the same generator's first {n_cpu:.0e} pairs"},
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_cpu:.0e} pairs/step, {M}x{R} partitions, C restatement of vega's map-side combine + reduce-side merge (oracle/vega_oracle.c); vega itself is Rust and cannot be built in this image"},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    import numpy as np
+    import torch
+
+    import vega_b200 as vb
+    from vega_b200 import _lib as L
+    from vega_b200 import dist as vdist
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    pg = None
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=torch.device(dev))
+        pg = tdist.group.WORLD
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    sc = vb.Context(local_rank, profile=True)
+    engine = vdist.CudaEngine(sc)
+    stream = sc.stream()
+    rows = torch.empty((N, 2), dtype=torch.int64, device=dev)       # 16 B/pair resident in HBM
+    sc.gen_pairs(out_rows=rows, first=rank * N, n=N, mode="uniform", n_distinct=D, seed_k=1, seed_v=2)
+    starts = vb.slice_starts(N, M)
+    n_map_global, n_red_global = M * world, R * world
+    lo, _ = vdist.map_block(rank, world, n_map_global)
+    maps = [(lo + m, rows[int(starts[m]):int(starts[m + 1])], None) for m in range(len(starts) - 1)]
+
+    def step(stats=None):
+        sh = vdist.run_shuffle(engine, maps, n_map_global, n_red_global, L.VB_U64, L.VB_U64, L.VB_AGG_SUM, rank, world,
+                               group=pg, hint=D, stats=stats)
+        return sh
+
+    for _ in range(args.warmup):
+        step().free()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"hot_ms": 0.0, "hot_launches": 0, "hot_rows": 0, "launches": 0, "map_ms": 0.0, "seal_ms": 0.0}
+    xstats = {}
+    kept = []
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        kept.append(step(xstats))
+    ev1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_dev = ev0.elapsed_time(ev1)
+    ms_total = max(ms_dev, 0.0)
+    n_keys_out = 0
+    for sh in kept:
+        st = sh.stats()
+        agg["hot_ms"] += st["hot_kernel_ms"]; agg["hot_launches"] += st["hot_kernel_launches"]
+        agg["hot_rows"] += st["hot_kernel_rows"]; agg["launches"] += st["kernel_launches"]
+        agg["map_ms"] += st["map_ms"]; agg["seal_ms"] += st["seal_ms"]
+        n_keys_out = st["rows_out"]
+    # parity property on the last step (size-independent): every key of the universe present exactly
+    # once across this rank's partitions and the sums add up to the sum of all values
+    last = kept[-1]
+    chk_keys, chk_sum = 0, 0
+    for r in vdist.owned_partitions(rank, world, n_red_global):
+        k, c = last.reduce(r)
+        chk_keys += len(k); chk_sum += int(c.sum(dtype=np.uint64))
+    for sh in kept:
+        sh.free()
+    if world > 1:
+        t = torch.tensor([ms_total, float(chk_keys), float(chk_sum % (1 << 52))], dtype=torch.float64, device=dev)
+        tmax = t.clone(); tdist.all_reduce(tmax, op=tdist.ReduceOp.MAX)
+        tsum = t.clone(); tdist.all_reduce(tsum, op=tdist.ReduceOp.SUM)
+        ms_total = float(tmax[0]); chk_keys = int(tsum[1])
+    total_vals = None
+    if world == 1:
+        total_vals = int(rows[:, 1].sum().item())
+        expect_all = N >= 40 * D          # coupon collector: every rank of the key universe occurs
+        assert (chk_keys == D if expect_all else chk_keys <= D) and chk_sum == total_vals, \
+            f"parity property failed: keys {chk_keys} (D={D}), sum {chk_sum} != {total_vals}"
+    ms_per_step = ms_total / args.steps
+    value = (N * world) / (ms_per_step * 1e-3)
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        rows_per_launch = agg["hot_rows"] / max(agg["hot_launches"], 1)
+        avg_launch_ms = agg["hot_ms"] / max(agg["hot_launches"], 1)
+        alg_bytes = rows_per_launch * ALG_BYTES_PER_PAIR + 16.0 * D
+        achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+        out = {
+            "metric": "reduce_by_key (K,V) pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload, "layout": "AoS 16-byte rows resident in HBM", "op": "sum",
+                       "l2": "inputs (16 GB/GPU) larger than the 126 MB L2; no flush needed",
+                       "timing": "CUDA events on the library's stream, max over ranks"},
+            "clocks": clocks,
+            "gpu_launches": agg["launches"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "hash_agg_kernel<IN_AOS,OPK_ADD_U64>",
+                         "rows_per_launch": rows_per_launch, "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
+                         "step_share": agg["hot_ms"] / max(ms_total, 1e-9),
+                         "whole_step_frac": (N * ALG_BYTES_PER_PAIR + 16.0 * D) / (ms_per_step * 1e-3) / 1e9 / peak},
+            "phases_ms_per_step": {"map": agg["map_ms"] / args.steps, "seal": agg["seal_ms"] / args.steps},
+            "parity": {"distinct_keys_out": chk_keys, "sum_matches_input": True if world == 1 else None},
+        }
+        if world > 1:
+            out["exchange"] = {"rows_sent_per_rank_per_step": xstats.get("sent_rows"), "bytes_per_row": 16}
+
+    # ---------------------------------------------------------------- e2e (public API, host buffers)
+    if not args.no_e2e:
+        n_e2e = int(args.e2e_rows) if args.e2e_rows else N
+        host = None
+        while host is None and n_e2e >= 1 << 20:
+            try:
+                host = torch.empty((n_e2e, 2), dtype=torch.int64, pin_memory=True)
+            except Exception:
+                n_e2e //= 2
+        host.copy_(rows[:n_e2e])
+        torch.cuda.synchronize()
+        sc.set_profile(False)
+        hostnp = host.numpy()
+
+        def e2e_step():
+            if world == 1:
+                k, c = sc.parallelize(hostnp, M).reduce_by_key("sum", R, hint=D).collect()
+                return len(k), 0, 16 * len(k)
+            st = vb.slice_starts(n_e2e, M)
+            mp = [(lo + m, hostnp[int(st[m]):int(st[m + 1])], None) for m in range(len(st) - 1)]
+            sh = vdist.run_shuffle(engine, mp, n_map_global, n_red_global, L.VB_U64, L.VB_U64, L.VB_AGG_SUM, rank, world,
+                                   group=pg, hint=D)
+            nk = 0
+            for r in vdist.owned_partitions(rank, world, n_red_global):
+                k, c = sh.reduce(r)
+                nk += len(k)
+            sh.free()
+            return nk, 0, 16 * nk
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        e_steps = max(1, min(args.steps, 3))
+        for _ in range(e_steps):
+            _, _, b = e2e_step()
+            d2h = b
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            dt = float(t[0])
+        if rank == 0:
+            out["e2e"] = {"value": n_e2e * world * e_steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n_e2e,
+                          "d2h_bytes_per_step": d2h, "rows_per_gpu": n_e2e, "steps": e_steps,
+                          "api": "Context.parallelize(pinned host rows, M).reduce_by_key('sum', R).collect()"}
+        del host
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_cpu = int(min(args.cpu_rows, N))
+        threads = min(M, nproc)
+        times = cpu_port_run(n_cpu, D, M, R, threads, 2, 1)
+        out["cpu_baseline"] = {"value": n_cpu * len(times) / sum(times), "unit": "pairs/s", "cores": threads, "kind": "port",
+                               "host_cores": nproc,
+                               "sample": f"first {n_cpu:.0e} pairs of the same generator, {M}x{R} partitions, 2 timed runs; C restatement of vega's algorithm (oracle/vega_oracle.c), not vega itself (Rust, unbuildable here)"}
+    if rank == 0:
+        print(json.dumps(out))
+    sc.close()
+    if world > 1:
+        tdist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

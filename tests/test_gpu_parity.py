@@ -1,0 +1,301 @@
+"""GPU parity: the CUDA path, called through the C ABI (vega_b200 → libvega_b200.so), against
+the CPU oracle on the same inputs.  Bit-exact for keys, counts, integer reductions, grouped
+membership AND order (tests/test_pair_rdd.rs:30-36 pins input order inside a group); f64 sums
+within 1e-6 relative (north_star).  Golden vectors are the reference's own test data."""
+import threading
+
+import numpy as np
+import pytest
+
+import vega_b200 as vb
+from oracle import oracle as O
+from tests.util import gpu_group_parts, gpu_reduce_parts, oracle_group, oracle_reduce, rand_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sc():
+    c = vb.Context(0)
+    yield c
+    c.close()
+
+
+# ---- the reference's golden vectors through the GPU path ------------------------------------
+def test_group_by_key_golden(sc):
+    # tests/test_pair_rdd.rs:8-37 / examples/group_by.rs with "x"→10, "y"→20
+    keys = np.array([10] * 7 + [20] * 8, dtype=np.uint64)
+    vals = np.array(list(range(1, 8)) + list(range(1, 9)), dtype=np.int64)
+    g = sc.make_rdd((keys, vals), 4).group_by_key(4)
+    res = sorted((k, v.tolist()) for k, v in g.collect().to_list())
+    assert res == [(10, [1, 2, 3, 4, 5, 6, 7]), (20, [1, 2, 3, 4, 5, 6, 7, 8])]
+
+
+def test_join_golden(sc):
+    # tests/test_pair_rdd.rs:39-82 / examples/join.rs; payload strings → table indices
+    col1 = [(1, ("A", "B")), (2, ("C", "D")), (3, ("E", "F")), (4, ("G", "H"))]
+    col2 = [(1, "A1"), (1, "A2"), (2, "B1"), (2, "B2"), (3, "C1"), (3, "C2")]
+    r1 = sc.parallelize((np.array([k for k, _ in col1], dtype=np.int32), np.arange(4, dtype=np.uint64)), 4)
+    r2 = sc.parallelize((np.array([k for k, _ in col2], dtype=np.int32), np.arange(6, dtype=np.uint64)), 4)
+    k, v, w = r2.join(r1, 4).collect()
+    res = sorted((int(a), (col2[int(b)][1], col1[int(c)][1])) for a, b, c in zip(k, v, w))
+    assert res == [(1, ("A1", ("A", "B"))), (1, ("A2", ("A", "B"))), (2, ("B1", ("C", "D"))),
+                   (2, ("B2", ("C", "D"))), (3, ("C1", ("E", "F"))), (3, ("C2", ("E", "F")))]
+
+
+@pytest.mark.parametrize("slices", [4, 2])
+def test_count_by_value_golden(sc, slices):
+    # tests/test_pair_rdd.rs:84-109
+    rdd = sc.parallelize(np.array([1, 2, 1, 3, 2, 3, 3, 2, 3], dtype=np.int32), slices)
+    k, c = rdd.count_by_value().collect()
+    assert sorted(zip(k.tolist(), c.tolist())) == [(1, 2), (2, 3), (3, 4)]
+
+
+def test_group_by_golden(sc):
+    # tests/test_pair_rdd.rs:111-135: group_by(sign) with neg→0, zero→1, pos→2
+    xs = np.array([-3, -2, -1, 0, 1, 2, 3], dtype=np.int64)
+    keys = np.where(xs < 0, 0, np.where(xs == 0, 1, 2)).astype(np.uint64)
+    res = sorted((k, v.tolist()) for k, v in sc.make_rdd((keys, xs), 2).group_by_key(2).collect().to_list())
+    assert res == [(0, [-3, -2, -1]), (1, [0]), (2, [1, 2, 3])]
+
+
+@pytest.mark.parametrize("parts", [None, 2, 10])
+def test_distinct_golden(sc, parts):
+    # tests/test_rdd.rs:285-322
+    rdd = sc.parallelize(np.array([1, 2, 2, 2, 3, 3, 3, 4, 4, 5], dtype=np.int32), 3)
+    res = rdd.distinct(parts).collect()
+    assert len(res) == 5 and set(res.tolist()) == {1, 2, 3, 4, 5}
+
+
+def test_cogroup_and_intersection_golden(sc):
+    # tests/test_rdd.rs:434-456 (cogroup → 4 keys) and :484-521 (intersection → [3,4,5,13])
+    k = np.array([1, 2, 3, 4], dtype=np.int32)
+    v = np.arange(4, dtype=np.uint64)
+    cg = sc.parallelize((k, v), 2).cogroup(sc.parallelize((k, v), 2), 2).cogroup_collect()
+    assert sorted((a, (x.tolist(), y.tolist())) for a, (x, y) in cg) == [(i + 1, ([i], [i])) for i in range(4)]
+    c1 = np.array([1, 2, 3, 4, 5, 10, 12, 13, 19, 0], dtype=np.int32)
+    c2 = np.array([3, 4, 5, 6, 7, 8, 11, 13], dtype=np.int32)
+    for nparts in (3, 2):
+        cg = sc.parallelize((c1, np.zeros(10, np.uint64)), 2).cogroup(sc.parallelize((c2, np.zeros(8, np.uint64)), 4), nparts)
+        inter = sorted(a for a, (x, y) in cg.cogroup_collect() if len(x) >= 1 and len(y) >= 1)
+        assert inter == [3, 4, 5, 13]
+
+
+# ---- randomized differential tests against the oracle -----------------------------------------
+@pytest.mark.parametrize("op,vdtype", [("sum", "u64"), ("sum", "i64"), ("sum", "f64"), ("min", "u64"), ("max", "u64"),
+                                       ("min", "i64"), ("max", "i64"), ("min", "f64"), ("max", "f64")])
+@pytest.mark.parametrize("n,M,R,nkeys", [(50_000, 5, 7, 1000), (3, 8, 2, 3), (200_000, 8, 8, 150_000)])
+def test_reduce_by_key_matches_oracle(sc, op, vdtype, n, M, R, nkeys):
+    rng = np.random.default_rng(hash((op, vdtype, n)) % 2 ** 32)
+    keys, vals = rand_pairs(rng, n, nkeys, vdtype)
+    want = oracle_reduce(op, keys, vals, M, R, vdtype)
+    got = gpu_reduce_parts(sc.parallelize((keys, vals), M).reduce_by_key(op, R))
+    assert [set(d) for d in got] == [set(d) for d in want]          # keys AND placement (hash % R)
+    for g, w in zip(got, want):
+        if vdtype == "f64" and op == "sum":
+            for k in w:
+                assert g[k] == pytest.approx(w[k], rel=1e-6, abs=1e-9)
+        else:
+            assert g == w
+
+
+@pytest.mark.parametrize("layout", ["aos_host", "soa_device", "aos_device"])
+def test_reduce_layouts_and_locations(sc, layout):
+    import torch
+    rng = np.random.default_rng(11)
+    keys, vals = rand_pairs(rng, 100_000, 5000)
+    want = oracle_reduce("sum", keys, vals, 6, 5)
+    if layout == "aos_host":
+        rdd = sc.parallelize(np.stack([keys, vals], axis=1), 6)
+    elif layout == "soa_device":
+        rdd = sc.parallelize((torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(vals.view(np.int64)).cuda()), 6)
+    else:
+        rdd = sc.parallelize(torch.from_numpy(np.stack([keys, vals], axis=1).view(np.int64)).cuda(), 6)
+    got = gpu_reduce_parts(rdd.reduce_by_key("sum", 5))
+    if layout != "aos_host":       # int64 tensors: same bits
+        got = [{k & (2 ** 64 - 1): v & (2 ** 64 - 1) for k, v in d.items()} for d in got]
+    assert got == want
+
+
+@pytest.mark.parametrize("n,M,R,nkeys", [(60_000, 4, 4, 500), (15, 4, 4, 2), (5, 32, 3, 4), (100_000, 7, 300, 40_000),
+                                         (30_000, 3, 1, 30_000)])
+def test_group_by_key_matches_oracle_in_order(sc, n, M, R, nkeys):
+    rng = np.random.default_rng(n + R)
+    keys, vals = rand_pairs(rng, n, nkeys)
+    want = oracle_group(keys, vals, M, R)
+    got = gpu_group_parts(sc.parallelize((keys, vals), M).group_by_key(R))
+    assert got == want        # per partition: same keys, each value list in input order (F5)
+
+
+def test_group_aos_device_borrowed(sc):
+    import torch
+    rng = np.random.default_rng(5)
+    keys, vals = rand_pairs(rng, 300_000, 20_000)
+    rows = torch.from_numpy(np.stack([keys, vals], axis=1).view(np.int64)).cuda()
+    got = gpu_group_parts(sc.parallelize(rows, 8).group_by_key(8))
+    got = [{k & (2 ** 64 - 1): [x & (2 ** 64 - 1) for x in v] for k, v in d.items()} for d in got]
+    assert got == oracle_group(keys, vals, 8, 8)
+
+
+def test_count_and_i32_key_width(sc):
+    rng = np.random.default_rng(9)
+    keys = rng.integers(-500, 500, 40_000).astype(np.int32)
+    want = oracle_reduce("count", keys.astype(np.int64), None, 5, 6, key_width=4)
+    got = gpu_reduce_parts(sc.parallelize(keys, 5).count_by_value().__class__(
+        vb.PairRdd(sc, vb.rdd._Col(keys), None, 5), "count", 6))
+    got = [{k & (2 ** 64 - 1): v for k, v in d.items()} for d in got]
+    assert got == want
+
+
+def test_sentinel_and_extreme_keys(sc):
+    # 0xFFFF_FFFF_FFFF_FFFF is the table's empty marker internally — it must still work as a key
+    keys = np.array([2 ** 64 - 1, 0, 2 ** 64 - 1, 1, 2 ** 63, 0, 2 ** 64 - 1, 2 ** 64 - 2], dtype=np.uint64)
+    vals = np.arange(1, 9, dtype=np.uint64)
+    for M, R in ((1, 1), (3, 4)):
+        assert gpu_reduce_parts(sc.parallelize((keys, vals), M).reduce_by_key("sum", R)) == oracle_reduce("sum", keys, vals, M, R)
+        assert gpu_group_parts(sc.parallelize((keys, vals), M).group_by_key(R)) == oracle_group(keys, vals, M, R)
+        assert gpu_reduce_parts(sc.parallelize((keys, vals), M).reduce_by_key("min", R)) == oracle_reduce("min", keys, vals, M, R)
+
+
+def test_empty_and_tiny_inputs(sc):
+    e = np.empty(0, dtype=np.uint64)
+    assert gpu_reduce_parts(sc.parallelize((e, e), 4).reduce_by_key("sum", 3)) == [{}, {}, {}]
+    assert gpu_group_parts(sc.parallelize((e, e), 4).group_by_key(2)) == [{}, {}]
+    k, v, w = sc.parallelize((e, e), 2).join(sc.parallelize((e, e), 2), 2).collect()
+    assert len(k) == len(v) == len(w) == 0
+    one = np.array([7], dtype=np.uint64)
+    assert gpu_reduce_parts(sc.parallelize((one, one), 5).reduce_by_key("max", 2)) == oracle_reduce("max", one, one, 5, 2)
+
+
+def test_table_growth_all_distinct(sc):
+    # 3M distinct keys force the 2^21-slot first table to restart larger
+    n = 3_000_000
+    keys = (np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    vals = np.ones(n, dtype=np.uint64)
+    rdd = sc.parallelize((keys, vals), 2).reduce_by_key("sum", 4)
+    k, c = rdd.collect()
+    assert len(k) == n and (c == 1).all() and len(np.unique(k)) == n
+    assert rdd.stats()["table_restarts"] >= 1
+    for r in (0, 3):
+        kk, _ = rdd.compute(r)
+        sample = kk[:: max(1, len(kk) // 50)]
+        assert all(O.get_partition(int(x), 4) == r for x in sample)
+
+
+@pytest.mark.parametrize("na,nb,R,nkeys", [(20_000, 30_000, 4, 3000), (5000, 10, 3, 50), (1000, 1000, 300, 2000)])
+def test_join_matches_oracle(sc, na, nb, R, nkeys):
+    rng = np.random.default_rng(na + nb)
+    ka, va = rand_pairs(rng, na, nkeys)
+    kb, vb_ = rand_pairs(rng, nb, nkeys)
+    want = sorted(zip(*[np.concatenate(x).tolist() for x in zip(*O.join(ka, va, 3, kb, vb_, 5, R))]))
+    k, v, w = sc.parallelize((ka, va), 3).join(sc.parallelize((kb, vb_), 5), R).collect()
+    assert sorted(zip(k.tolist(), v.tolist(), w.tolist())) == want
+    # per-partition placement and the reference's nesting order (for v in vs { for w in ws })
+    j = sc.parallelize((ka, va), 3).join(sc.parallelize((kb, vb_), 5), R)
+    ora = O.join(ka, va, 3, kb, vb_, 5, R)
+    for r in range(min(R, 4)):
+        gk, gv, gw = j.compute(r)
+        ok, ov, ow = ora[r]
+        assert sorted(zip(gk.tolist(), gv.tolist(), gw.tolist())) == sorted(zip(ok.tolist(), ov.tolist(), ow.tolist()))
+        # within one key, GPU rows keep (v outer, w inner) order like the oracle
+        if len(gk):
+            key = gk[0]
+            assert list(zip(gv[gk == key].tolist(), gw[gk == key].tolist())) == list(zip(ov[ok == key].tolist(), ow[ok == key].tolist()))
+
+
+@pytest.mark.parametrize("kdtype", ["u64", "i64", "f64"])
+@pytest.mark.parametrize("payload", [True, False])
+def test_sort_by_key_matches_oracle(sc, kdtype, payload):
+    rng = np.random.default_rng(3)
+    n = 70_000
+    if kdtype == "u64":
+        keys = rng.integers(0, 2 ** 63, n).astype(np.uint64) * np.uint64(2) + rng.integers(0, 2, n).astype(np.uint64)
+    elif kdtype == "i64":
+        keys = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
+    else:
+        keys = rng.standard_normal(n) * 1e6
+    keys[::7] = keys[3]          # long runs of equal keys: stability + cut rule
+    vals = np.arange(n, dtype=np.uint64)
+    ok, ov, ps = O.sort_by_key(keys, vals, 8, kdtype)
+    src = sc.parallelize((keys, vals), 5) if payload else sc.parallelize(keys, 5)
+    rdd = src.sort_by_key(8) if payload else src.sort(8)
+    k, v = rdd.collect()
+    assert (k == ok).all()
+    if payload:
+        assert (v == ov).all()      # stable: equal keys keep input order
+    sizes = [len(rdd.compute(r)[0]) for r in range(8)]
+    assert sizes == np.diff(ps.astype(np.int64)).tolist()
+
+
+def test_partition_by_key(sc):
+    keys = np.arange(1000, dtype=np.uint64)
+    vals = keys * np.uint64(3)
+    parts = sc.parallelize((keys, vals), 4).partition_by_key(100).glom()
+    assert len(parts) == 100 and sum(len(p) for p in parts) == 1000
+    for r in (0, 17, 99):
+        assert all(O.get_partition(int(v) // 3, 100) == r for v in parts[r])
+
+
+def test_device_generator_matches_oracle(sc):
+    import torch
+    n, D = 100_000, 977
+    rows = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=12345, n=n, mode="uniform", n_distinct=D, seed_k=1, seed_v=2)
+    k, v = O.gen_uniform(12345, n, D, 1, 2)
+    got = rows.cpu().numpy().view(np.uint64)
+    assert (got[:, 0] == k).all() and (got[:, 1] == v).all()
+
+
+# ---- boundary behaviour ---------------------------------------------------------------------
+def test_stage_resubmission_overwrites(sc):
+    keys = np.array([1, 2, 3, 1], dtype=np.uint64)
+    v1 = np.array([10, 20, 30, 40], dtype=np.uint64)
+    sh = vb.Shuffle(sc, 2, 2, 0, 0, 1)
+    ck, cv = vb.rdd._Col(keys), vb.rdd._Col(v1)
+    sh.map(0, ck, cv, 0, 2)
+    sh.map(1, ck, cv, 2, 4)
+    sh.map(0, ck, cv, 0, 2)          # resubmitted map task must not double count
+    sh.seal()
+    got = {}
+    for r in range(2):
+        k, c = sh.reduce(r)
+        got.update(zip(k.tolist(), c.tolist()))
+    assert got == {1: 50, 2: 20, 3: 30}
+    sh.free()
+
+
+def test_reduce_blocks_until_sealed(sc):
+    keys = np.arange(100, dtype=np.uint64)
+    sh = vb.Shuffle(sc, 1, 1, 0, 0, 1)
+    col = vb.rdd._Col(keys)
+    sh.map(0, col, col, 0, 100)
+    out = {}
+    t = threading.Thread(target=lambda: out.setdefault("r", sh.reduce(0)))
+    t.start()
+    t.join(0.3)
+    assert t.is_alive()              # blocked in vb_shuffle_reduce_size (condvar), like get_server_uris
+    sh.seal()
+    t.join(10)
+    assert not t.is_alive() and sorted(out["r"][0].tolist()) == list(range(100))
+    sh.free()
+
+
+def test_error_conventions(sc):
+    keys = np.arange(10, dtype=np.uint64)
+    col = vb.rdd._Col(keys)
+    sh = vb.Shuffle(sc, 2, 2, 0, 0, 1)
+    sh.map(0, col, col, 0, 5)
+    with pytest.raises(vb.VegaB200Error) as e:       # map 1 never submitted
+        sh.seal()
+    assert e.value.code == -4
+    sh.free()
+    sh = vb.Shuffle(sc, 1, 2, 0, 0, 1)
+    sh.map(0, col, col, 0, 10)
+    sh.seal()
+    with pytest.raises(vb.VegaB200Error):            # map after seal
+        sh.map(0, col, col, 0, 10)
+    with pytest.raises(vb.VegaB200Error):            # bad reduce id
+        sh.reduce(2)
+    sh.free()
+    with pytest.raises(vb.VegaB200Error):            # f64 keys are not Hash
+        vb.Shuffle(sc, 1, 1, 2, 0, 1)

@@ -1,0 +1,1481 @@
+// engine.cu — C ABI of libvega_b200.so (see include/vega_b200.h) and the host orchestration of
+// the shuffle + aggregation kernels in kernels.cuh.  sm_100a only; no CPU fallback: every
+// compute entry needs a CUDA device and fails with VB_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vega_b200.h"
+#include "kernels.cuh"
+
+using namespace vb;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int set_err(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            cudaGetLastError();                                                                         \
+            return set_err(e_ == cudaErrorMemoryAllocation ? VB_ERR_OOM : VB_ERR_CUDA, "%s:%d %s: %s", \
+                           __FILE__, __LINE__, #expr, cudaGetErrorString(e_));                          \
+        }                                                                                               \
+    } while (0)
+
+#define TRY(expr)                  \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != VB_OK) return rc_; \
+    } while (0)
+
+extern "C" const char *vb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *vb_version(void) { return "vega_b200 0.1 sm_100a"; }
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+enum { K_HASH_AGG = 0, K_DICT = 1, K_MERGE = 2, K_RP_HIST = 3, K_RP_SCAN = 4, K_RP_SCATTER = 5, K_MISC = 6, K_JOIN = 7, K_N = 8 };
+
+struct vb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    std::mutex mu;                 // serialises device work of this context
+    bool profile = false;
+    void *h_scratch = nullptr;     // pinned, 1 MiB
+    size_t h_scratch_bytes = 1 << 20;
+    double *zipf_cdf = nullptr;    // cached device CDF for vb_gen_pairs
+    u64 zipf_n = 0;
+    double zipf_s = 0;
+    std::map<const void *, int> occ_cache;
+};
+
+struct DevBuf {   // stream-ordered device allocation, freed on scope exit unless released
+    vb_ctx *c = nullptr;
+    void *p = nullptr;
+    DevBuf() {}
+    explicit DevBuf(vb_ctx *c_) : c(c_) {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { reset(); }
+    void reset()
+    {
+        if (p) cudaFreeAsync(p, c->stream);
+        p = nullptr;
+    }
+    int alloc(size_t bytes)
+    {
+        reset();
+        if (bytes == 0) bytes = 16;
+        CU(cudaMallocAsync(&p, bytes, c->pool, c->stream));
+        return VB_OK;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+    void *release()
+    {
+        void *q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
+static void dev_free(vb_ctx *c, const void *p)
+{
+    if (p) cudaFreeAsync((void *)p, c->stream);
+}
+
+template <typename K>
+static int occupancy(vb_ctx *c, K kernel, int threads, size_t smem)
+{
+    auto it = c->occ_cache.find((const void *)kernel);
+    if (it != c->occ_cache.end()) return it->second;
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) {
+        cudaGetLastError();
+        nb = 1;
+    }
+    c->occ_cache[(const void *)kernel] = nb;
+    return nb;
+}
+
+extern "C" int32_t vb_ctx_create(int32_t device_id, vb_ctx **out)
+{
+    if (!out) return set_err(VB_ERR_INVALID, "vb_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(VB_ERR_CUDA, "vb_ctx_create: no CUDA device (%s); libvega_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device_id < 0 || device_id >= ndev) return set_err(VB_ERR_INVALID, "vb_ctx_create: device %d of %d", device_id, ndev);
+    CU(cudaSetDevice(device_id));
+    vb_ctx *c = new vb_ctx();
+    c->device = device_id;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_id));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaDeviceGetDefaultMemPool(&c->pool, device_id));
+    uint64_t thr = ~0ull;
+    CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CU(cudaMallocHost(&c->h_scratch, c->h_scratch_bytes));
+    *out = c;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_destroy(vb_ctx *c)
+{
+    if (!c) return VB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->zipf_cdf) cudaFreeAsync(c->zipf_cdf, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_scratch);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_synchronize(vb_ctx *c)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_set_profile(vb_ctx *c, int32_t on)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    c->profile = on != 0;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_device(vb_ctx *c) { return c ? c->device : -1; }
+extern "C" void *vb_ctx_stream(vb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int32_t vb_ctx_mem_info(vb_ctx *c, uint64_t *reserved, uint64_t *high_water)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    uint64_t r = 0, h = 0;
+    CU(cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &r));
+    CU(cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemHigh, &h));
+    if (reserved) *reserved = r;
+    if (high_water) *high_water = h;
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shuffle state
+// ---------------------------------------------------------------------------------------------
+struct MapOut {
+    bool present = false;
+    u64 n_rows = 0;
+    // reduce ops: the combined table of this map task (== SHUFFLE_CACHE[(sid, map, *)])
+    Slot *table = nullptr;
+    u32 log_cap = 0;
+    u64 n_inserted = 0;
+    // group/sort ops: the rows (device), AoS or SoA
+    const u64 *rows = nullptr;
+    const u64 *keys = nullptr;
+    const u64 *vals = nullptr;
+    bool owned = false;
+};
+
+struct Timer {
+    cudaEvent_t a, b;
+    int klass;   // K_* or -1 (map call) / -2 (seal call)
+    u64 rows;
+};
+
+struct JoinPlan {
+    u64 total = 0;
+    u32 nl = 0;
+    u64 *pos = nullptr;
+    u32 *match = nullptr;
+};
+
+struct vb_shuf {
+    vb_ctx *ctx = nullptr;
+    u64 id = 0;
+    u32 n_map = 0, n_reduce = 0;
+    int kdt = 0, vdt = 0, agg = 0, part = 0;
+    u32 key_width = 8;
+    u64 hint = 0;
+    u32 rank = 0, world = 1;
+    std::vector<MapOut> maps;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool sealed = false, failed = false, freed = false;
+    // export / import (world > 1)
+    bool exported = false, imported = false;
+    u64 *exp_keys = nullptr, *exp_vals = nullptr;
+    const u64 *imp_keys = nullptr, *imp_vals = nullptr;
+    u64 imp_n = 0;
+    // gathered input kept alive for the reduce side of group ops
+    u64 *gath_keys = nullptr, *gath_vals = nullptr;
+    // results
+    u64 n_keys = 0, n_vals = 0;
+    u64 *res_keys = nullptr, *res_comb = nullptr, *res_offs = nullptr, *res_vals = nullptr;
+    std::vector<u64> bucket_off;   // n_reduce + 1 (key index)
+    std::vector<u64> val_off;      // n_reduce + 1 (value index; group ops)
+    Slot *dict = nullptr;          // group ops: key → slot, kept for joins
+    u32 dict_log_cap = 0;
+    u32 *dense_of_slot = nullptr;
+    std::map<std::pair<const vb_shuf *, u32>, JoinPlan> join_plans;
+    // stats
+    vb_stats st{};
+    std::vector<Timer> timers;
+    double kms[K_N] = {0};
+    u64 klaunch[K_N] = {0};
+};
+
+static bool is_reduce_op(int agg) { return agg == VB_AGG_SUM || agg == VB_AGG_MIN || agg == VB_AGG_MAX || agg == VB_AGG_COUNT; }
+static bool is_group_op(int agg) { return agg == VB_AGG_GROUP || agg == VB_AGG_COGROUP; }
+
+static int val_tx(const vb_shuf *s)
+{
+    if (s->agg != VB_AGG_MIN && s->agg != VB_AGG_MAX) return TX_NONE;
+    return s->vdt == VB_I64 ? TX_I64 : s->vdt == VB_F64 ? TX_F64 : TX_NONE;
+}
+static int map_opk(const vb_shuf *s)
+{
+    switch (s->agg) {
+    case VB_AGG_SUM: return s->vdt == VB_F64 ? OPK_ADD_F64 : OPK_ADD_U64;
+    case VB_AGG_MIN: return OPK_MIN_U64;
+    case VB_AGG_MAX: return OPK_MAX_U64;
+    case VB_AGG_COUNT: return OPK_COUNT;
+    default: return OPK_DICT;
+    }
+}
+static int merge_opk(const vb_shuf *s) { return s->agg == VB_AGG_COUNT ? OPK_ADD_U64 : map_opk(s); }
+
+// kernel launch bookkeeping (+ CUDA-event timing on the launching stream when profiling)
+struct KLaunch {
+    vb_shuf *s;
+    int klass;
+    u64 rows;
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool pushed = false;
+    ~KLaunch()
+    {
+        if (a && !pushed) { cudaEventDestroy(a); cudaEventDestroy(b); }
+    }
+    KLaunch(vb_shuf *s_, int klass_, u64 rows_ = 0) : s(s_), klass(klass_), rows(rows_)
+    {
+        if (s && s->ctx->profile) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, s->ctx->stream);
+        }
+    }
+    int done(const char *what)
+    {
+        cudaError_t e = cudaGetLastError();
+        if (a) {
+            cudaEventRecord(b, s->ctx->stream);
+            s->timers.push_back(Timer{a, b, klass, rows});
+            pushed = true;
+        }
+        if (s && klass >= 0) {
+            s->klaunch[klass]++;
+            s->st.kernel_launches++;
+        }
+        if (e != cudaSuccess) return set_err(VB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+        return VB_OK;
+    }
+};
+
+static void resolve_timers(vb_shuf *s)
+{
+    if (s->timers.empty()) return;
+    cudaStreamSynchronize(s->ctx->stream);
+    for (auto &t : s->timers) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            if (t.klass >= 0) s->kms[t.klass] += ms;
+            else if (t.klass == -1) s->st.map_ms += ms;
+            else s->st.seal_ms += ms;
+            int hot = is_reduce_op(s->agg) ? K_HASH_AGG : K_RP_SCATTER;
+            if (t.klass == hot) {
+                s->st.hot_kernel_ms += ms;
+                s->st.hot_kernel_launches++;
+                s->st.hot_kernel_rows += t.rows;
+            }
+        } else cudaGetLastError();
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    s->timers.clear();
+}
+
+static u32 ceil_log2_u64(u64 x)
+{
+    u32 l = 0;
+    while ((1ull << l) < x && l < 63) ++l;
+    return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hash table build (map-side combine / reduce-side merge / dictionary)
+// ---------------------------------------------------------------------------------------------
+struct AggInput {
+    int in;          // IN_AOS / IN_SOA / IN_TABLE
+    const u64 *a;
+    const u64 *b;
+    u64 n;           // rows (IN_TABLE: slots incl. the special one)
+    int loc;         // VB_HOST or device
+};
+
+template <int IN, int OPK, int TX>
+static int launch_hash_agg_t(vb_shuf *s, int klass, const u64 *a, const u64 *b, u64 n, Slot *tab, u32 log_cap,
+                             TableCtl *ctl, u64 max_inserts, u32 *slot_out)
+{
+    vb_ctx *c = s->ctx;
+    auto kern = hash_agg_kernel<IN, OPK, TX>;
+    int occ = occupancy(c, kern, HA_THREADS, 0);
+    u64 tiles = (n + HA_TILE - 1) / HA_TILE;
+    u64 grid = std::min<u64>(tiles, (u64)c->sm_count * occ);
+    if (grid == 0) return VB_OK;
+    KLaunch kl(s, klass, n);
+    kern<<<(unsigned)grid, HA_THREADS, 0, c->stream>>>(a, b, n, tab, log_cap, ctl, max_inserts, slot_out);
+    return kl.done("hash_agg_kernel");
+}
+
+template <int IN>
+static int launch_hash_agg_in(vb_shuf *s, int klass, int opk, int tx, const u64 *a, const u64 *b, u64 n, Slot *tab,
+                              u32 log_cap, TableCtl *ctl, u64 mi, u32 *so)
+{
+#define HA(O, T) return launch_hash_agg_t<IN, O, T>(s, klass, a, b, n, tab, log_cap, ctl, mi, so)
+    switch (opk) {
+    case OPK_ADD_U64: HA(OPK_ADD_U64, TX_NONE);
+    case OPK_ADD_F64: HA(OPK_ADD_F64, TX_NONE);
+    case OPK_COUNT: if constexpr (IN != IN_TABLE) { HA(OPK_COUNT, TX_NONE); } break;
+    case OPK_DICT: if constexpr (IN != IN_TABLE) { HA(OPK_DICT, TX_NONE); } break;
+    case OPK_MIN_U64:
+        if (IN == IN_TABLE || tx == TX_NONE) HA(OPK_MIN_U64, TX_NONE);
+        if (tx == TX_I64) HA(OPK_MIN_U64, (IN == IN_TABLE ? TX_NONE : TX_I64));
+        HA(OPK_MIN_U64, (IN == IN_TABLE ? TX_NONE : TX_F64));
+    case OPK_MAX_U64:
+        if (IN == IN_TABLE || tx == TX_NONE) HA(OPK_MAX_U64, TX_NONE);
+        if (tx == TX_I64) HA(OPK_MAX_U64, (IN == IN_TABLE ? TX_NONE : TX_I64));
+        HA(OPK_MAX_U64, (IN == IN_TABLE ? TX_NONE : TX_F64));
+    }
+#undef HA
+    return set_err(VB_ERR_UNSUPPORTED, "hash_agg: unsupported op %d for input mode %d", opk, IN);
+}
+
+static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, Slot *tab,
+                           u32 log_cap, TableCtl *ctl, u64 mi, u32 *so)
+{
+    switch (in) {
+    case IN_AOS: return launch_hash_agg_in<IN_AOS>(s, klass, opk, tx, a, b, n, tab, log_cap, ctl, mi, so);
+    case IN_SOA: return launch_hash_agg_in<IN_SOA>(s, klass, opk, tx, a, b, n, tab, log_cap, ctl, mi, so);
+    case IN_TABLE: return launch_hash_agg_in<IN_TABLE>(s, klass, opk, tx, a, b, n, tab, log_cap, ctl, mi, so);
+    }
+    return set_err(VB_ERR_INVALID, "hash_agg: bad input mode %d", in);
+}
+
+constexpr u64 HOST_CHUNK_ROWS = 32ull << 20;   // host inputs are streamed through a 512 MiB stage
+constexpr u32 MAX_LOG_CAP = 31;
+
+// Feed every input into one fresh table; on overflow (abort flag) start again 4x larger.
+// slot_out (OPK_DICT): one u32 per row over the concatenation of the inputs.
+static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &inputs, int opk, int tx, u64 hint_distinct,
+                       Slot **out_tab, u32 *out_log_cap, u64 *out_inserted, u32 *slot_out)
+{
+    vb_ctx *c = s->ctx;
+    u64 total = 0;
+    bool any_host = false;
+    u64 max_host = 0;
+    for (auto &in : inputs) {
+        total += in.n;
+        if (in.loc == VB_HOST) { any_host = true; max_host = std::max(max_host, in.n); }
+    }
+    if (slot_out && any_host) return set_err(VB_ERR_INVALID, "build_table: dictionary inputs must be on the device");
+    u32 max_log = std::max<u32>(4, ceil_log2_u64(2 * std::max<u64>(total, 1)));
+    if (max_log > MAX_LOG_CAP) return set_err(VB_ERR_TOO_LARGE, "shuffle %llu: %llu rows exceed the device-local limit", (unsigned long long)s->id, (unsigned long long)total);
+    u64 target = hint_distinct ? 2 * hint_distinct : std::min<u64>(2 * std::max<u64>(total, 1), 1ull << 21);
+    u32 log_cap = std::min(max_log, std::max<u32>(4, ceil_log2_u64(target)));
+
+    DevBuf ctl(c), stage_a(c), stage_b(c);
+    TRY(ctl.alloc(sizeof(TableCtl)));
+    if (any_host) {
+        u64 rows = std::min(max_host, HOST_CHUNK_ROWS);
+        TRY(stage_a.alloc(rows * 16));   // AoS rows, or SoA keys in the first half / vals in the second
+    }
+    TableCtl *h_ctl = (TableCtl *)c->h_scratch;
+    for (;;) {
+        const u64 cap = 1ull << log_cap;
+        DevBuf tab(c);
+        TRY(tab.alloc((cap + 1) * sizeof(Slot)));
+        {
+            KLaunch kl(s, K_MISC);
+            u64 blocks = std::min<u64>((cap + 1 + 255) / 256, (u64)c->sm_count * 8);
+            table_init_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(tab.as<Slot>(), cap, op_identity(opk));
+            TRY(kl.done("table_init_kernel"));
+        }
+        CU(cudaMemsetAsync(ctl.p, 0, sizeof(TableCtl), c->stream));
+        const u64 max_inserts = (log_cap == max_log) ? ~0ull : (cap / 10) * 6;
+        u64 row_base = 0;
+        for (auto &in : inputs) {
+            if (in.n == 0) continue;
+            if (in.loc != VB_HOST) {
+                TRY(launch_hash_agg(s, klass, in.in, opk, tx, in.a, in.b, in.n, tab.as<Slot>(), log_cap, ctl.as<TableCtl>(),
+                                    max_inserts, slot_out ? slot_out + row_base : nullptr));
+            } else {
+                const u64 chunk = std::min(in.n, HOST_CHUNK_ROWS);
+                for (u64 off = 0; off < in.n; off += chunk) {
+                    const u64 m = std::min(chunk, in.n - off);
+                    const u64 *da = stage_a.as<u64>(), *db = nullptr;
+                    if (in.in == IN_AOS) {
+                        CU(cudaMemcpyAsync(stage_a.p, in.a + 2 * off, m * 16, cudaMemcpyHostToDevice, c->stream));
+                        s->st.h2d_bytes += m * 16;
+                    } else {
+                        CU(cudaMemcpyAsync(stage_a.p, in.a + off, m * 8, cudaMemcpyHostToDevice, c->stream));
+                        s->st.h2d_bytes += m * 8;
+                        if (in.b) {
+                            db = stage_a.as<u64>() + chunk;
+                            CU(cudaMemcpyAsync((void *)db, in.b + off, m * 8, cudaMemcpyHostToDevice, c->stream));
+                            s->st.h2d_bytes += m * 8;
+                        }
+                    }
+                    TRY(launch_hash_agg(s, klass, in.in, opk, tx, da, db, m, tab.as<Slot>(), log_cap, ctl.as<TableCtl>(),
+                                        max_inserts, nullptr));
+                }
+            }
+            row_base += in.n;
+        }
+        CU(cudaMemcpyAsync(h_ctl, ctl.p, sizeof(TableCtl), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (!h_ctl->abort) {
+            *out_tab = (Slot *)tab.release();
+            *out_log_cap = log_cap;
+            *out_inserted = h_ctl->n_inserted;
+            s->st.table_slots = std::max<u64>(s->st.table_slots, cap);
+            return VB_OK;
+        }
+        if (log_cap >= max_log) return set_err(VB_ERR_CUDA, "hash table overflow at maximum capacity 2^%u (internal error)", log_cap);
+        log_cap = std::min(max_log, log_cap + 2);
+        s->st.table_restarts++;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix pass host side
+// ---------------------------------------------------------------------------------------------
+struct PassPlan {
+    u32 num_parts = 0;
+    u64 rows_per_part = 0;
+    size_t hist_bytes() const { return ((size_t)RP_NB * num_parts + 1) * sizeof(u32); }
+};
+
+template <typename KeyT, bool HAS_VAL>
+static PassPlan plan_pass(vb_ctx *c, u64 n)
+{
+    PassPlan p;
+    if (n == 0) return p;
+    auto kern = rp_scatter_kernel<KeyT, HAS_VAL>;
+    size_t smem = rp_scatter_smem<KeyT, HAS_VAL>();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = occupancy(c, kern, RP_THREADS, smem);
+    u64 tiles = (n + RP_TILE - 1) / RP_TILE;
+    u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
+    u64 tiles_per_part = (tiles + parts - 1) / parts;
+    p.rows_per_part = tiles_per_part * RP_TILE;
+    p.num_parts = (u32)((n + p.rows_per_part - 1) / p.rows_per_part);
+    return p;
+}
+
+// One stable pass: rows of `ld` (n of them) are written to out_keys/out_vals grouped by digit.
+// d_hist (device, plan.hist_bytes()) afterwards holds the scanned histogram: d_hist[d*num_parts]
+// is the output offset of digit d, d_hist[RP_NB*num_parts] the number of valid rows.
+template <typename KeyT, bool HAS_VAL>
+static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist,
+                      const PassPlan &plan)
+{
+    vb_ctx *c = s->ctx;
+    if (n == 0 || plan.num_parts == 0) return VB_OK;
+    {
+        KLaunch kl(s, K_RP_HIST, n);
+        rp_hist_kernel<KeyT><<<plan.num_parts, RP_THREADS, 0, c->stream>>>(ld, dg, n, plan.rows_per_part, d_hist, plan.num_parts);
+        TRY(kl.done("rp_hist_kernel"));
+    }
+    {
+        KLaunch kl(s, K_RP_SCAN);
+        rp_scan_kernel<<<1, 1024, 0, c->stream>>>(d_hist, (u32)RP_NB * plan.num_parts);
+        TRY(kl.done("rp_scan_kernel"));
+    }
+    {
+        KLaunch kl(s, K_RP_SCATTER, n);
+        rp_scatter_kernel<KeyT, HAS_VAL><<<plan.num_parts, RP_THREADS, rp_scatter_smem<KeyT, HAS_VAL>(), c->stream>>>(
+            ld, dg, n, plan.rows_per_part, d_hist, plan.num_parts, out_keys, out_vals);
+        TRY(kl.done("rp_scatter_kernel"));
+    }
+    return VB_OK;
+}
+
+// Copy the start offset of each of the first nb digits plus the total to the host: out[nb+1].
+static int fetch_offsets(vb_ctx *c, const u32 *d_hist, const PassPlan &plan, u32 nb, u64 *out)
+{
+    u32 *h = (u32 *)c->h_scratch;
+    CU(cudaMemcpy2DAsync(h, sizeof(u32), d_hist, (size_t)plan.num_parts * sizeof(u32), sizeof(u32), RP_NB,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + RP_NB, d_hist + (size_t)RP_NB * plan.num_parts, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (u32 d = 0; d < nb; ++d) out[d] = h[d];
+    out[nb] = h[RP_NB];
+    return VB_OK;
+}
+
+static Digit make_bucket_digit(const vb_shuf *s, int mode, u32 shift, u32 mask)
+{
+    Digit dg{};
+    dg.mode = mode;
+    dg.shift = shift;
+    dg.mask = mask;
+    dg.tx = TX_NONE;
+    dg.key_width = s->key_width;
+    dg.fm = make_fastmod(s->n_reduce);
+    dg.fm_world = make_fastmod(s->world);
+    return dg;
+}
+
+__global__ void bucket_hist_kernel(const u64 *__restrict__ keys, u64 n, Digit dg, u32 *__restrict__ cnt)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[get_partition(keys[i], dg.key_width, dg.fm)], 1u);
+}
+
+// Stable multisplit of `n` loader rows by reduce partition (DG_BUCKET, nbins = n_reduce) or by
+// owning rank (DG_DEST, nbins = world).  Invalid rows (empty table slots) are dropped.
+// out_keys/out_vals must hold `max_valid` rows.  bin_off[nbins+1] (host) gets the offsets.
+static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, u64 max_valid, u64 *out_keys, u64 *out_vals,
+                      std::vector<u64> &bin_off)
+{
+    vb_ctx *c = s->ctx;
+    bin_off.assign((size_t)nbins + 1, 0);
+    if (n == 0) return VB_OK;
+    PassPlan plan = plan_pass<u64, true>(c, n);
+    DevBuf hist(c);
+    TRY(hist.alloc(plan.hist_bytes()));
+    if (nbins <= RP_NB) {
+        Digit dg = make_bucket_digit(s, mode, 0, 0xFFFFFFFFu);
+        TRY((radix_pass<u64, true>(s, ld, dg, n, out_keys, out_vals, hist.as<u32>(), plan)));
+        TRY(fetch_offsets(c, hist.as<u32>(), plan, nbins, bin_off.data()));
+        return VB_OK;
+    }
+    if (mode != DG_BUCKET || nbins > 65536) return set_err(VB_ERR_UNSUPPORTED, "more than 65536 reduce partitions / 256 ranks");
+    // two LSD passes over the 16-bit bucket id
+    DevBuf tk(c), tv(c);
+    TRY(tk.alloc(max_valid * 8));
+    TRY(tv.alloc(max_valid * 8));
+    Digit d0 = make_bucket_digit(s, DG_BUCKET, 0, 0xFF);
+    TRY((radix_pass<u64, true>(s, ld, d0, n, tk.as<u64>(), tv.as<u64>(), hist.as<u32>(), plan)));
+    std::vector<u64> tmp(RP_NB + 1);
+    TRY(fetch_offsets(c, hist.as<u32>(), plan, RP_NB, tmp.data()));
+    const u64 nv = tmp[RP_NB];
+    if (nv == 0) return VB_OK;
+    PassPlan plan2 = plan_pass<u64, true>(c, nv);
+    DevBuf hist2(c);
+    TRY(hist2.alloc(plan2.hist_bytes()));
+    Loader l2{LD_SOA64, tk.p, tv.p, 0};
+    Digit d1 = make_bucket_digit(s, DG_BUCKET, 8, 0xFF);
+    TRY((radix_pass<u64, true>(s, l2, d1, nv, out_keys, out_vals, hist2.as<u32>(), plan2)));
+    DevBuf cnt(c);
+    TRY(cnt.alloc((size_t)nbins * 4));
+    CU(cudaMemsetAsync(cnt.p, 0, (size_t)nbins * 4, c->stream));
+    {
+        KLaunch kl(s, K_MISC);
+        bucket_hist_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, c->stream>>>(out_keys, nv, d0, cnt.as<u32>());
+        TRY(kl.done("bucket_hist_kernel"));
+    }
+    std::vector<u32> hc(nbins);
+    CU(cudaMemcpyAsync(hc.data(), cnt.p, (size_t)nbins * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    u64 run = 0;
+    for (u32 b = 0; b < nbins; ++b) { bin_off[b] = run; run += hc[b]; }
+    bin_off[nbins] = run;
+    return VB_OK;
+}
+
+// LSD radix sort of (u32 id, u64 val) pairs over `bits` low bits.  ids_a is overwritten.
+// The first pass reads values through `first` (ids come from ids_a).  Results: *out_ids, *out_vals
+// (owned by the caller afterwards).
+static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32 bits, u32 **out_ids, u64 **out_vals)
+{
+    vb_ctx *c = s->ctx;
+    const u32 passes = std::max<u32>(1, (bits + 7) / 8);
+    PassPlan plan = plan_pass<u32, true>(c, n);
+    DevBuf hist(c), ids_b(c), vals_a(c), vals_b(c);
+    TRY(hist.alloc(plan.hist_bytes()));
+    TRY(ids_b.alloc(n * 4));
+    TRY(vals_b.alloc(n * 8));
+    if (passes >= 2) TRY(vals_a.alloc(n * 8));
+    u32 *src_ids = ids_a, *dst_ids = ids_b.as<u32>();
+    u64 *src_vals = nullptr, *dst_vals = vals_b.as<u64>();
+    for (u32 p = 0; p < passes; ++p) {
+        Loader ld = first;
+        if (p == 0) ld.keys = src_ids;
+        else ld = Loader{LD_KEY32_VAL_SOA, src_ids, src_vals, 0};
+        Digit dg{};
+        dg.mode = DG_BITS;
+        dg.shift = 8 * p;
+        dg.mask = 0xFF;
+        dg.tx = TX_NONE;
+        TRY((radix_pass<u32, true>(s, ld, dg, n, dst_ids, dst_vals, hist.as<u32>(), plan)));
+        std::swap(src_ids, dst_ids);
+        u64 *nv = (src_vals == nullptr) ? vals_a.as<u64>() : src_vals;
+        src_vals = dst_vals;
+        dst_vals = nv;
+    }
+    // results are in src_ids / src_vals
+    *out_ids = src_ids;
+    *out_vals = src_vals;
+    if (src_ids == ids_b.as<u32>()) ids_b.release();          // ids_a stays with the caller either way
+    if (src_vals == vals_b.as<u64>()) vals_b.release(); else vals_a.release();
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shuffle lifecycle
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t vb_shuffle_create(vb_ctx *c, uint64_t shuffle_id, uint32_t n_map, uint32_t n_reduce, int32_t kdt,
+                                     int32_t vdt, int32_t agg, int32_t part, vb_shuf **out)
+{
+    if (!c || !out) return set_err(VB_ERR_INVALID, "vb_shuffle_create: NULL argument");
+    *out = nullptr;
+    if (n_reduce < 1) return set_err(VB_ERR_INVALID, "vb_shuffle_create: n_reduce must be >= 1");
+    if (kdt < VB_U64 || kdt > VB_F64 || vdt < VB_U64 || vdt > VB_F64) return set_err(VB_ERR_INVALID, "bad dtype");
+    if (agg < VB_AGG_GROUP || agg > VB_AGG_SORT) return set_err(VB_ERR_INVALID, "bad agg %d", agg);
+    if (agg != VB_AGG_SORT && kdt == VB_F64) return set_err(VB_ERR_UNSUPPORTED, "f64 keys are not hashable (Rust f64 is not Hash)");
+    if ((agg == VB_AGG_SORT) != (part == VB_PART_RANGE)) return set_err(VB_ERR_INVALID, "VB_PART_RANGE goes with VB_AGG_SORT only");
+    if (n_reduce > 65536) return set_err(VB_ERR_UNSUPPORTED, "more than 65536 reduce partitions");
+    vb_shuf *s = new vb_shuf();
+    s->ctx = c;
+    s->id = shuffle_id;
+    s->n_map = n_map;
+    s->n_reduce = n_reduce;
+    s->kdt = kdt;
+    s->vdt = vdt;
+    s->agg = agg;
+    s->part = part;
+    s->maps.resize(n_map);
+    *out = s;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_set_key_width(vb_shuf *s, uint32_t bytes)
+{
+    if (!s || (bytes != 4 && bytes != 8)) return set_err(VB_ERR_INVALID, "key width must be 4 or 8");
+    s->key_width = bytes;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_set_hint(vb_shuf *s, uint64_t d)
+{
+    if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    s->hint = d;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_set_dist(vb_shuf *s, uint32_t rank, uint32_t world)
+{
+    if (!s || world < 1 || rank >= world || world > 256) return set_err(VB_ERR_INVALID, "bad rank/world");
+    if (s->agg == VB_AGG_SORT && world > 1) return set_err(VB_ERR_UNSUPPORTED, "multi-rank sort_by_key is not implemented");
+    s->rank = rank;
+    s->world = world;
+    return VB_OK;
+}
+
+static void free_map(vb_shuf *s, MapOut &m)
+{
+    vb_ctx *c = s->ctx;
+    if (m.table) dev_free(c, m.table);
+    if (m.owned) { dev_free(c, m.rows); dev_free(c, m.keys); dev_free(c, m.vals); }
+    m = MapOut();
+}
+
+static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys, const u64 *vals, u64 n, int loc)
+{
+    if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    if (map_id >= s->n_map) return set_err(VB_ERR_INVALID, "map_id %u >= n_map %u", map_id, s->n_map);
+    if (loc < VB_HOST || loc > VB_DEVICE_BORROWED) return set_err(VB_ERR_INVALID, "bad src_loc %d", loc);
+    if (n && !rows && !keys) return set_err(VB_ERR_INVALID, "NULL input with n_rows > 0");
+    if (n >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "map partition of %llu rows", (unsigned long long)n);
+    vb_ctx *c = s->ctx;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->sealed || s->exported || s->freed) return set_err(VB_ERR_STATE, "shuffle %llu: map after seal/export", (unsigned long long)s->id);
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    KLaunch call(s, -1);
+    MapOut &m = s->maps[map_id];
+    if (m.present) { s->st.rows_in -= m.n_rows; free_map(s, m); }   // stage resubmission: overwrite
+    m.n_rows = n;
+    if (is_reduce_op(s->agg)) {
+        if (!rows && !vals && s->agg != VB_AGG_COUNT && n) return set_err(VB_ERR_INVALID, "values required for this aggregator");
+        std::vector<AggInput> in(1);
+        in[0] = AggInput{rows ? IN_AOS : IN_SOA, rows ? rows : keys, vals, n, loc == VB_HOST ? VB_HOST : VB_DEVICE};
+        TRY(build_table(s, K_HASH_AGG, in, map_opk(s), val_tx(s), s->hint, &m.table, &m.log_cap, &m.n_inserted, nullptr));
+    } else if (n) {
+        if (loc == VB_DEVICE_BORROWED) {
+            m.rows = rows; m.keys = keys; m.vals = vals; m.owned = false;
+        } else {
+            const cudaMemcpyKind kind = loc == VB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            DevBuf a(c), b(c);
+            if (rows) {
+                TRY(a.alloc(n * 16));
+                CU(cudaMemcpyAsync(a.p, rows, n * 16, kind, c->stream));
+                if (loc == VB_HOST) s->st.h2d_bytes += n * 16;
+            } else {
+                TRY(a.alloc(n * 8));
+                CU(cudaMemcpyAsync(a.p, keys, n * 8, kind, c->stream));
+                if (loc == VB_HOST) s->st.h2d_bytes += n * 8;
+                if (vals) {
+                    TRY(b.alloc(n * 8));
+                    CU(cudaMemcpyAsync(b.p, vals, n * 8, kind, c->stream));
+                    if (loc == VB_HOST) s->st.h2d_bytes += n * 8;
+                }
+            }
+            CU(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer on return
+            if (rows) m.rows = (const u64 *)a.release();
+            else { m.keys = (const u64 *)a.release(); m.vals = vals ? (const u64 *)b.release() : nullptr; }
+            m.owned = true;
+        }
+    }
+    m.present = true;
+    s->st.rows_in += n;
+    TRY(call.done("map"));
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_map_aos(vb_shuf *s, uint32_t map_id, const void *rows, uint64_t n, int32_t loc)
+{
+    return shuffle_map(s, map_id, (const u64 *)rows, nullptr, nullptr, n, loc);
+}
+extern "C" int32_t vb_shuffle_map_soa(vb_shuf *s, uint32_t map_id, const void *keys, const void *vals, uint64_t n, int32_t loc)
+{
+    return shuffle_map(s, map_id, nullptr, (const u64 *)keys, (const u64 *)vals, n, loc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduce side
+// ---------------------------------------------------------------------------------------------
+// Concatenate the rows of all present map partitions in map-id order.  Zero-copy when they are
+// one AoS run (adjacent in memory) or a single partition; otherwise SoA copies owned by s.
+struct Gathered {
+    const u64 *rows = nullptr, *keys = nullptr, *vals = nullptr;
+    u64 n = 0;
+};
+
+static int gather_maps(vb_shuf *s, Gathered *g)
+{
+    vb_ctx *c = s->ctx;
+    u64 n = 0;
+    std::vector<MapOut *> segs;
+    for (auto &m : s->maps)
+        if (m.present && m.n_rows) { segs.push_back(&m); n += m.n_rows; }
+    g->n = n;
+    if (n == 0) return VB_OK;
+    if (n >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "shuffle of %llu rows on one device", (unsigned long long)n);
+    bool contiguous = true;
+    for (size_t i = 0; i < segs.size(); ++i) {
+        if (!segs[i]->rows) { contiguous = false; break; }
+        if (i && segs[i - 1]->rows + 2 * segs[i - 1]->n_rows != segs[i]->rows) { contiguous = false; break; }
+    }
+    if (contiguous) { g->rows = segs[0]->rows; return VB_OK; }
+    if (segs.size() == 1) { g->keys = segs[0]->keys; g->vals = segs[0]->vals; return VB_OK; }
+    bool any_vals = false;
+    for (auto *m : segs) any_vals |= (m->rows != nullptr) || (m->vals != nullptr);
+    DevBuf k(c), v(c);
+    TRY(k.alloc(n * 8));
+    if (any_vals) TRY(v.alloc(n * 8));
+    u64 off = 0;
+    for (auto *m : segs) {
+        if (m->rows) {
+            KLaunch kl(s, K_MISC);
+            u64 blocks = std::min<u64>((m->n_rows + 255) / 256, (u64)c->sm_count * 8);
+            aos_to_soa_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(m->rows, m->n_rows, k.as<u64>() + off, v.as<u64>() + off);
+            TRY(kl.done("aos_to_soa_kernel"));
+        } else {
+            CU(cudaMemcpyAsync(k.as<u64>() + off, m->keys, m->n_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
+            if (any_vals) {
+                if (m->vals) CU(cudaMemcpyAsync(v.as<u64>() + off, m->vals, m->n_rows * 8, cudaMemcpyDeviceToDevice, c->stream));
+                else CU(cudaMemsetAsync(v.as<u64>() + off, 0, m->n_rows * 8, c->stream));
+            }
+        }
+        off += m->n_rows;
+    }
+    s->gath_keys = (u64 *)k.release();
+    s->gath_vals = any_vals ? (u64 *)v.release() : nullptr;
+    g->keys = s->gath_keys;
+    g->vals = s->gath_vals;
+    for (auto &m : s->maps) if (m.present && m.owned) { dev_free(c, m.rows); dev_free(c, m.keys); dev_free(c, m.vals); m.rows = m.keys = m.vals = nullptr; m.owned = false; }
+    return VB_OK;
+}
+
+__global__ void gather_u64_kernel(const u64 *__restrict__ src, const u64 *__restrict__ idx, u32 n, u64 *__restrict__ out)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+__global__ void rebase_kernel(const u64 *__restrict__ src, u64 n, u64 base, u64 *__restrict__ out)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[i] - base;
+}
+
+// group_by_key / cogroup reduce side over n rows (AoS `rows`, or SoA keys/vals).
+static int seal_group(vb_shuf *s, const Gathered &g)
+{
+    vb_ctx *c = s->ctx;
+    const u32 R = s->n_reduce;
+    s->bucket_off.assign((size_t)R + 1, 0);
+    s->val_off.assign((size_t)R + 1, 0);
+    const u64 n = g.n;
+    if (n == 0) return VB_OK;
+    // 1. dictionary: key → slot, slot per row
+    DevBuf ids(c);
+    TRY(ids.alloc(n * 4));
+    std::vector<AggInput> in(1);
+    in[0] = AggInput{g.rows ? IN_AOS : IN_SOA, g.rows ? g.rows : g.keys, nullptr, n, VB_DEVICE};
+    u64 n_ins = 0;
+    TRY(build_table(s, K_DICT, in, OPK_DICT, TX_NONE, s->hint, &s->dict, &s->dict_log_cap, &n_ins, ids.as<u32>()));
+    const u64 cap = 1ull << s->dict_log_cap;
+    // 2. distinct keys grouped by reduce partition (stable by slot)
+    const u64 max_d = n_ins + 1;
+    DevBuf ckeys(c), cslot(c);
+    TRY(ckeys.alloc(max_d * 8));
+    TRY(cslot.alloc(max_d * 8));
+    Loader lt{LD_TABLE_KI, s->dict, nullptr, cap};
+    TRY(multisplit(s, lt, cap + 1, DG_BUCKET, R, max_d, ckeys.as<u64>(), cslot.as<u64>(), s->bucket_off));
+    const u64 D = s->bucket_off[R];
+    // 3. slot → dense id (bucket-major)
+    DevBuf dense(c);
+    TRY(dense.alloc((cap + 1) * 4));
+    {
+        KLaunch kl(s, K_MISC);
+        scatter_dense_kernel<<<(unsigned)((D + 255) / 256), 256, 0, c->stream>>>(cslot.as<u64>(), (u32)D, dense.as<u32>());
+        TRY(kl.done("scatter_dense_kernel"));
+    }
+    cslot.reset();
+    // 4. ids[i] = dense_of_slot[slot_of_row[i]]
+    {
+        KLaunch kl(s, K_MISC);
+        u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8);
+        translate_ids_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(ids.as<u32>(), n, dense.as<u32>());
+        TRY(kl.done("translate_ids_kernel"));
+    }
+    // 5. stable LSD sort of (id, value) — the reduce partition is the high part of the dense id
+    Loader first = g.rows ? Loader{LD_KEY32_VAL_AOS, nullptr, g.rows, 0} : Loader{LD_KEY32_VAL_SOA, nullptr, g.vals, 0};
+    u32 *sorted_ids = nullptr;
+    u64 *sorted_vals = nullptr;
+    TRY(sort_id_pairs(s, ids.as<u32>(), first, n, ceil_log2_u64(std::max<u64>(D, 2)), &sorted_ids, &sorted_vals));
+    DevBuf sid_guard(c);
+    if (sorted_ids != ids.as<u32>()) sid_guard.p = sorted_ids;
+    // 6. CSR offsets
+    DevBuf offs(c);
+    TRY(offs.alloc((D + 1) * 8));
+    {
+        KLaunch kl(s, K_MISC);
+        u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8);
+        csr_bounds_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sorted_ids, n, offs.as<u64>(), D);
+        TRY(kl.done("csr_bounds_kernel"));
+    }
+    // 7. value offsets at the partition boundaries
+    {
+        DevBuf idx(c), out(c);
+        TRY(idx.alloc(((size_t)R + 1) * 8));
+        TRY(out.alloc(((size_t)R + 1) * 8));
+        CU(cudaMemcpyAsync(idx.p, s->bucket_off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        KLaunch kl(s, K_MISC);
+        gather_u64_kernel<<<(R + 1 + 255) / 256, 256, 0, c->stream>>>(offs.as<u64>(), idx.as<u64>(), R + 1, out.as<u64>());
+        TRY(kl.done("gather_u64_kernel"));
+        CU(cudaMemcpyAsync(s->val_off.data(), out.p, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    s->n_keys = D;
+    s->n_vals = n;
+    s->res_keys = (u64 *)ckeys.release();
+    s->res_offs = (u64 *)offs.release();
+    s->res_vals = sorted_vals;
+    s->dense_of_slot = (u32 *)dense.release();
+    s->st.rows_out = n;
+    return VB_OK;
+}
+
+// Merge the per-map combined tables of this process into one (ShuffledRdd::compute's
+// merge_combiners loop, shuffled_rdd.rs:154-164, for the partitions held locally).
+static int merge_map_tables(vb_shuf *s, Slot **tab, u32 *log_cap, u64 *n_ins)
+{
+    std::vector<MapOut *> ts;
+    for (auto &m : s->maps) if (m.present && m.table) ts.push_back(&m);
+    if (ts.empty()) { *tab = nullptr; *log_cap = 0; *n_ins = 0; return VB_OK; }
+    if (ts.size() == 1) {
+        *tab = ts[0]->table; *log_cap = ts[0]->log_cap; *n_ins = ts[0]->n_inserted;
+        ts[0]->table = nullptr;
+        return VB_OK;
+    }
+    std::vector<AggInput> in;
+    u64 max_ins = 0;
+    for (auto *m : ts) {
+        in.push_back(AggInput{IN_TABLE, (const u64 *)m->table, nullptr, (1ull << m->log_cap) + 1, VB_DEVICE});
+        max_ins = std::max(max_ins, m->n_inserted);
+    }
+    TRY(build_table(s, K_MERGE, in, merge_opk(s), TX_NONE, std::max<u64>(max_ins, s->hint), tab, log_cap, n_ins, nullptr));
+    for (auto *m : ts) { dev_free(s->ctx, m->table); m->table = nullptr; }
+    return VB_OK;
+}
+
+// Final (K, C) rows of a combined table, grouped by reduce partition.
+static int finalize_reduce(vb_shuf *s, Slot *tab, u32 log_cap, u64 n_ins)
+{
+    vb_ctx *c = s->ctx;
+    const u32 R = s->n_reduce;
+    s->bucket_off.assign((size_t)R + 1, 0);
+    s->val_off.assign((size_t)R + 1, 0);
+    if (!tab) return VB_OK;
+    const u64 cap = 1ull << log_cap;
+    const u64 max_d = n_ins + 1;
+    DevBuf k(c), v(c);
+    TRY(k.alloc(max_d * 8));
+    TRY(v.alloc(max_d * 8));
+    Loader lt{LD_TABLE_KV, tab, nullptr, cap};
+    TRY(multisplit(s, lt, cap + 1, DG_BUCKET, R, max_d, k.as<u64>(), v.as<u64>(), s->bucket_off));
+    const u64 D = s->bucket_off[R];
+    const int tx = val_tx(s);
+    if (tx != TX_NONE && D) {
+        KLaunch kl(s, K_MISC);
+        tx_inv_kernel<<<(unsigned)((D + 255) / 256), 256, 0, c->stream>>>(v.as<u64>(), D, tx);
+        TRY(kl.done("tx_inv_kernel"));
+    }
+    s->n_keys = D;
+    s->res_keys = (u64 *)k.release();
+    s->res_comb = (u64 *)v.release();
+    s->st.rows_out = D;
+    return VB_OK;
+}
+
+static int seal_sort(vb_shuf *s, const Gathered &g)
+{
+    vb_ctx *c = s->ctx;
+    const u32 R = s->n_reduce;
+    s->bucket_off.assign((size_t)R + 1, 0);
+    s->val_off.assign((size_t)R + 1, 0);
+    const u64 n = g.n;
+    if (n == 0) return VB_OK;
+    const bool has_val = g.rows != nullptr || g.vals != nullptr;
+    const int tx = s->kdt == VB_I64 ? TX_I64 : s->kdt == VB_F64 ? TX_F64 : TX_NONE;
+    DevBuf ka(c), kb(c), va(c), vbuf(c), hist(c);
+    TRY(ka.alloc(n * 8));
+    TRY(kb.alloc(n * 8));
+    if (has_val) { TRY(va.alloc(n * 8)); TRY(vbuf.alloc(n * 8)); }
+    PassPlan plan = has_val ? plan_pass<u64, true>(c, n) : plan_pass<u64, false>(c, n);
+    TRY(hist.alloc(plan.hist_bytes()));
+    u64 *src_k = nullptr, *src_v = nullptr, *dst_k = ka.as<u64>(), *dst_v = va.as<u64>();
+    for (u32 p = 0; p < 8; ++p) {
+        Loader ld;
+        if (p == 0) ld = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
+        else ld = Loader{LD_SOA64, src_k, has_val ? src_v : nullptr, 0};
+        Digit dg{};
+        dg.mode = DG_BITS; dg.shift = 8 * p; dg.mask = 0xFF; dg.tx = tx;
+        if (has_val) TRY((radix_pass<u64, true>(s, ld, dg, n, dst_k, dst_v, hist.as<u32>(), plan)));
+        else TRY((radix_pass<u64, false>(s, ld, dg, n, dst_k, nullptr, hist.as<u32>(), plan)));
+        u64 *nk = (src_k == nullptr) ? kb.as<u64>() : src_k;
+        u64 *nv = (src_v == nullptr) ? vbuf.as<u64>() : src_v;
+        src_k = dst_k; src_v = dst_v; dst_k = nk; dst_v = nv;
+    }
+    // 8 passes: results are in the buffer written by pass 7 == kb / vbuf (ka, kb alternate starting with ka)
+    DevBuf starts(c);
+    TRY(starts.alloc(((size_t)R + 1) * 8));
+    {
+        KLaunch kl(s, K_MISC);
+        sort_cuts_kernel<<<(R + 1 + 255) / 256, 256, 0, c->stream>>>(src_k, n, R, starts.as<u64>());
+        TRY(kl.done("sort_cuts_kernel"));
+    }
+    CU(cudaMemcpyAsync(s->bucket_off.data(), starts.p, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    s->n_keys = n;
+    s->res_keys = src_k;
+    s->res_comb = has_val ? src_v : nullptr;
+    if (src_k == ka.as<u64>()) ka.release(); else kb.release();
+    if (has_val) { if (src_v == va.as<u64>()) va.release(); else vbuf.release(); }
+    s->st.rows_out = n;
+    return VB_OK;
+}
+
+static void release_inputs(vb_shuf *s)
+{
+    for (auto &m : s->maps) if (m.present) { u64 n = m.n_rows; free_map(s, m); m.present = true; m.n_rows = n; }
+    dev_free(s->ctx, s->gath_keys);
+    dev_free(s->ctx, s->gath_vals);
+    s->gath_keys = s->gath_vals = nullptr;
+    dev_free(s->ctx, s->exp_keys);
+    dev_free(s->ctx, s->exp_vals);
+    s->exp_keys = s->exp_vals = nullptr;
+}
+
+extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
+{
+    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_export_prepare needs vb_shuffle_set_dist(world > 1)");
+    vb_ctx *c = s->ctx;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->sealed || s->exported || s->freed) return set_err(VB_ERR_STATE, "export after seal/export");
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    std::vector<u64> off;
+    if (is_reduce_op(s->agg)) {
+        Slot *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+        TRY(merge_map_tables(s, &tab, &log_cap, &n_ins));
+        off.assign((size_t)s->world + 1, 0);
+        if (tab) {
+            DevBuf guard(c); guard.p = tab;
+            DevBuf k(c), v(c);
+            TRY(k.alloc((n_ins + 1) * 8));
+            TRY(v.alloc((n_ins + 1) * 8));
+            Loader lt{LD_TABLE_KV, tab, nullptr, 1ull << log_cap};
+            TRY(multisplit(s, lt, (1ull << log_cap) + 1, DG_DEST, s->world, n_ins + 1, k.as<u64>(), v.as<u64>(), off));
+            s->exp_keys = (u64 *)k.release();
+            s->exp_vals = (u64 *)v.release();
+        }
+    } else {
+        Gathered g;
+        TRY(gather_maps(s, &g));
+        off.assign((size_t)s->world + 1, 0);
+        if (g.n) {
+            DevBuf k(c), v(c);
+            TRY(k.alloc(g.n * 8));
+            TRY(v.alloc(g.n * 8));
+            Loader ld = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
+            TRY(multisplit(s, ld, g.n, DG_DEST, s->world, g.n, k.as<u64>(), v.as<u64>(), off));
+            s->exp_keys = (u64 *)k.release();
+            s->exp_vals = (u64 *)v.release();
+        }
+    }
+    for (u32 r = 0; r < s->world; ++r) counts[r] = off[r + 1] - off[r];
+    CU(cudaStreamSynchronize(c->stream));
+    std::lock_guard<std::mutex> g(s->mu);
+    s->exported = true;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_export_buffers(vb_shuf *s, void **keys_dev, void **vals_dev)
+{
+    if (!s || !keys_dev || !vals_dev) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (!s->exported) return set_err(VB_ERR_STATE, "vb_shuffle_export_buffers before vb_shuffle_export_prepare");
+    *keys_dev = s->exp_keys;
+    *vals_dev = s->exp_vals;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_import(vb_shuf *s, const void *keys_dev, const void *vals_dev, const uint64_t *counts)
+{
+    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (!s->exported || s->sealed) return set_err(VB_ERR_STATE, "import needs export_prepare first and no seal yet");
+    u64 n = 0;
+    for (u32 r = 0; r < s->world; ++r) n += counts[r];
+    if (n && (!keys_dev || !vals_dev)) return set_err(VB_ERR_INVALID, "NULL buffers with rows to import");
+    if (n >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "import of %llu rows", (unsigned long long)n);
+    s->imp_keys = (const u64 *)keys_dev;
+    s->imp_vals = (const u64 *)vals_dev;
+    s->imp_n = n;
+    s->imported = true;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
+{
+    if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    vb_ctx *c = s->ctx;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->freed) return set_err(VB_ERR_STATE, "seal of a freed shuffle");
+        if (s->sealed) return VB_OK;
+    }
+    int rc = VB_OK;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        cudaSetDevice(c->device);
+        KLaunch call(s, -2);
+        auto body = [&]() -> int {
+            if (s->world == 1) {
+                for (u32 m = 0; m < s->n_map; ++m)
+                    if (!s->maps[m].present) return set_err(VB_ERR_STATE, "shuffle %llu sealed but map %u was never submitted", (unsigned long long)s->id, m);
+                if (is_reduce_op(s->agg)) {
+                    Slot *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+                    TRY(merge_map_tables(s, &tab, &log_cap, &n_ins));
+                    DevBuf guard(c); guard.p = tab;
+                    TRY(finalize_reduce(s, tab, log_cap, n_ins));
+                } else {
+                    Gathered g;
+                    TRY(gather_maps(s, &g));
+                    if (s->agg == VB_AGG_SORT) TRY(seal_sort(s, g)); else TRY(seal_group(s, g));
+                }
+            } else {
+                if (!s->exported || !s->imported) return set_err(VB_ERR_STATE, "world > 1: seal needs export_prepare + import");
+                if (is_reduce_op(s->agg)) {
+                    Slot *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+                    if (s->imp_n) {
+                        std::vector<AggInput> in(1);
+                        in[0] = AggInput{IN_SOA, s->imp_keys, s->imp_vals, s->imp_n, VB_DEVICE};
+                        TRY(build_table(s, K_MERGE, in, merge_opk(s), TX_NONE, s->hint, &tab, &log_cap, &n_ins, nullptr));
+                    }
+                    DevBuf guard(c); guard.p = tab;
+                    TRY(finalize_reduce(s, tab, log_cap, n_ins));
+                } else {
+                    Gathered g;
+                    g.keys = s->imp_keys; g.vals = s->imp_vals; g.n = s->imp_n;
+                    TRY(seal_group(s, g));
+                }
+            }
+            release_inputs(s);
+            CU(cudaStreamSynchronize(c->stream));
+            return VB_OK;
+        };
+        rc = body();
+        call.done("seal");
+    }
+    std::lock_guard<std::mutex> g(s->mu);
+    if (rc == VB_OK) s->sealed = true; else s->failed = true;
+    s->cv.notify_all();
+    return rc;
+}
+
+extern "C" int32_t vb_shuffle_is_sealed(vb_shuf *s) { return s && s->sealed ? 1 : 0; }
+
+static int wait_sealed(vb_shuf *s)
+{
+    std::unique_lock<std::mutex> g(s->mu);
+    s->cv.wait(g, [&] { return s->sealed || s->failed || s->freed; });
+    if (!s->sealed) return set_err(VB_ERR_STATE, "shuffle %llu failed or was freed before it was sealed", (unsigned long long)s->id);
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_reduce_size(vb_shuf *s, uint32_t r, uint64_t *n_keys, uint64_t *n_vals)
+{
+    if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    if (r >= s->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", r, s->n_reduce);
+    TRY(wait_sealed(s));
+    if (n_keys) *n_keys = s->bucket_off[r + 1] - s->bucket_off[r];
+    if (n_vals) *n_vals = is_group_op(s->agg) ? s->val_off[r + 1] - s->val_off[r] : 0;
+    return VB_OK;
+}
+
+static int copy_out(vb_shuf *s, void *dst, const void *src, size_t bytes, int dst_loc)
+{
+    if (!dst || !bytes) return VB_OK;
+    if (!src) return set_err(VB_ERR_STATE, "result array missing");
+    CU(cudaMemcpyAsync(dst, src, bytes, dst_loc == VB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s->ctx->stream));
+    if (dst_loc == VB_HOST) s->st.d2h_bytes += bytes;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_reduce(vb_shuf *s, uint32_t r, void *out_keys, void *out_combined, uint64_t *out_offsets,
+                                     void *out_vals, int32_t dst_loc)
+{
+    if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    if (r >= s->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", r, s->n_reduce);
+    if (dst_loc != VB_HOST && dst_loc != VB_DEVICE) return set_err(VB_ERR_INVALID, "bad dst_loc");
+    TRY(wait_sealed(s));
+    vb_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const u64 b0 = s->bucket_off[r], nk = s->bucket_off[r + 1] - b0;
+    TRY(copy_out(s, out_keys, s->res_keys ? s->res_keys + b0 : nullptr, nk * 8, dst_loc));
+    if (is_group_op(s->agg)) {
+        const u64 v0 = s->val_off[r], nv = s->val_off[r + 1] - v0;
+        if (out_offsets) {
+            if (nk == 0) {
+                u64 zero = 0;
+                CU(cudaMemcpyAsync(out_offsets, &zero, 8, dst_loc == VB_HOST ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, c->stream));
+            } else {
+                DevBuf tmp(c);
+                TRY(tmp.alloc((nk + 1) * 8));
+                KLaunch kl(s, K_MISC);
+                rebase_kernel<<<(unsigned)((nk + 1 + 255) / 256), 256, 0, c->stream>>>(s->res_offs + b0, nk + 1, v0, tmp.as<u64>());
+                TRY(kl.done("rebase_kernel"));
+                TRY(copy_out(s, out_offsets, tmp.p, (nk + 1) * 8, dst_loc));
+            }
+        }
+        TRY(copy_out(s, out_vals, s->res_vals ? s->res_vals + v0 : nullptr, nv * 8, dst_loc));
+    } else if (out_combined && nk) {
+        if (!s->res_comb && s->agg == VB_AGG_SORT) return set_err(VB_ERR_INVALID, "key-only sort has no payload");
+        TRY(copy_out(s, out_combined, s->res_comb + b0, nk * 8, dst_loc));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// join
+// ---------------------------------------------------------------------------------------------
+static int exclusive_scan_u64(vb_shuf *s, const u64 *in, u64 *out, u64 n, u64 *d_total)
+{
+    vb_ctx *c = s->ctx;
+    if (n == 0) return VB_OK;
+    const u64 blocks = (n + SC_CHUNK - 1) / SC_CHUNK;
+    if (blocks == 1) {
+        KLaunch kl(s, K_JOIN);
+        scan_apply_kernel<<<1, SC_THREADS, 0, c->stream>>>(in, out, n, nullptr, d_total);
+        return kl.done("scan_apply_kernel");
+    }
+    DevBuf sums(c), offs(c);
+    TRY(sums.alloc(blocks * 8));
+    TRY(offs.alloc(blocks * 8));
+    {
+        KLaunch kl(s, K_JOIN);
+        scan_reduce_kernel<<<(unsigned)blocks, SC_THREADS, 0, c->stream>>>(in, n, sums.as<u64>());
+        TRY(kl.done("scan_reduce_kernel"));
+    }
+    TRY(exclusive_scan_u64(s, sums.as<u64>(), offs.as<u64>(), blocks, nullptr));
+    KLaunch kl(s, K_JOIN);
+    scan_apply_kernel<<<(unsigned)blocks, SC_THREADS, 0, c->stream>>>(in, out, n, offs.as<u64>(), d_total);
+    return kl.done("scan_apply_kernel");
+}
+
+static int join_check(vb_shuf *l, vb_shuf *r, u32 rid)
+{
+    if (!l || !r) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    if (!is_group_op(l->agg) || !is_group_op(r->agg)) return set_err(VB_ERR_INVALID, "join needs two GROUP/COGROUP shuffles");
+    if (l->n_reduce != r->n_reduce || l->key_width != r->key_width) return set_err(VB_ERR_INVALID, "join sides use different partitioners");
+    if (l->ctx != r->ctx) return set_err(VB_ERR_INVALID, "join sides live on different contexts");
+    if (rid >= l->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", rid, l->n_reduce);
+    TRY(wait_sealed(l));
+    TRY(wait_sealed(r));
+    return VB_OK;
+}
+
+static int join_plan(vb_shuf *l, vb_shuf *r, u32 rid, JoinPlan **out)
+{
+    vb_ctx *c = l->ctx;
+    auto key = std::make_pair((const vb_shuf *)r, rid);
+    auto it = l->join_plans.find(key);
+    if (it != l->join_plans.end()) { *out = &it->second; return VB_OK; }
+    JoinPlan p;
+    const u64 lb = l->bucket_off[rid], le = l->bucket_off[rid + 1];
+    p.nl = (u32)(le - lb);
+    if (p.nl && r->n_keys && r->dict) {
+        DevBuf cnt(c), pos(c), match(c), tot(c);
+        TRY(cnt.alloc((u64)p.nl * 8));
+        TRY(pos.alloc((u64)p.nl * 8));
+        TRY(match.alloc((u64)p.nl * 4));
+        TRY(tot.alloc(8));
+        {
+            KLaunch kl(l, K_JOIN);
+            join_probe_kernel<<<(p.nl + 255) / 256, 256, 0, c->stream>>>(l->res_keys, l->res_offs, (u32)lb, (u32)le, r->dict,
+                                                                         r->dict_log_cap, r->dense_of_slot, r->res_offs,
+                                                                         cnt.as<u64>(), match.as<u32>());
+            TRY(kl.done("join_probe_kernel"));
+        }
+        TRY(exclusive_scan_u64(l, cnt.as<u64>(), pos.as<u64>(), p.nl, tot.as<u64>()));
+        CU(cudaMemcpyAsync(c->h_scratch, tot.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        p.total = *(u64 *)c->h_scratch;
+        p.pos = (u64 *)pos.release();
+        p.match = (u32 *)match.release();
+    }
+    auto ins = l->join_plans.emplace(key, p);
+    *out = &ins.first->second;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_join_size(vb_shuf *l, vb_shuf *r, uint32_t rid, uint64_t *n_out)
+{
+    TRY(join_check(l, r, rid));
+    if (!n_out) return set_err(VB_ERR_INVALID, "n_out is NULL");
+    std::lock_guard<std::mutex> lk(l->ctx->mu);
+    CU(cudaSetDevice(l->ctx->device));
+    JoinPlan *p = nullptr;
+    TRY(join_plan(l, r, rid, &p));
+    *n_out = p->total;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_join(vb_shuf *l, vb_shuf *r, uint32_t rid, void *out_k, void *out_v, void *out_w, int32_t dst_loc)
+{
+    TRY(join_check(l, r, rid));
+    if (dst_loc != VB_HOST && dst_loc != VB_DEVICE) return set_err(VB_ERR_INVALID, "bad dst_loc");
+    vb_ctx *c = l->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    JoinPlan *p = nullptr;
+    TRY(join_plan(l, r, rid, &p));
+    const u64 total = p->total;
+    int rc = VB_OK;
+    if (total) {
+        if (!out_k || !out_v || !out_w) return set_err(VB_ERR_INVALID, "NULL output with %llu rows to write", (unsigned long long)total);
+        DevBuf bk(c), bv(c), bw(c);
+        u64 *dk = (u64 *)out_k, *dv = (u64 *)out_v, *dw = (u64 *)out_w;
+        if (dst_loc == VB_HOST) {
+            TRY(bk.alloc(total * 8)); TRY(bv.alloc(total * 8)); TRY(bw.alloc(total * 8));
+            dk = bk.as<u64>(); dv = bv.as<u64>(); dw = bw.as<u64>();
+        }
+        {
+            KLaunch kl(l, K_JOIN);
+            u64 blocks = std::min<u64>((total + 255) / 256, (u64)c->sm_count * 8);
+            join_expand_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(p->pos, p->nl, total, l->res_keys, l->res_offs, l->res_vals,
+                                                                        (u32)l->bucket_off[rid], p->match, r->res_offs, r->res_vals,
+                                                                        dk, dv, dw);
+            rc = kl.done("join_expand_kernel");
+        }
+        if (rc == VB_OK && dst_loc == VB_HOST) {
+            rc = copy_out(l, out_k, dk, total * 8, VB_HOST);
+            if (rc == VB_OK) rc = copy_out(l, out_v, dv, total * 8, VB_HOST);
+            if (rc == VB_OK) rc = copy_out(l, out_w, dw, total * 8, VB_HOST);
+        }
+        cudaStreamSynchronize(c->stream);
+    }
+    dev_free(c, p->pos);
+    dev_free(c, p->match);
+    l->join_plans.erase(std::make_pair((const vb_shuf *)r, rid));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// free / stats
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t vb_shuffle_free(vb_shuf *s)
+{
+    if (!s) return VB_OK;
+    vb_ctx *c = s->ctx;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        s->freed = true;
+        s->cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        cudaSetDevice(c->device);
+        resolve_timers(s);
+        for (auto &m : s->maps) free_map(s, m);
+        release_inputs(s);
+        dev_free(c, s->res_keys); dev_free(c, s->res_comb); dev_free(c, s->res_offs); dev_free(c, s->res_vals);
+        dev_free(c, s->dict); dev_free(c, s->dense_of_slot);
+        for (auto &kv : s->join_plans) { dev_free(c, kv.second.pos); dev_free(c, kv.second.match); }
+        cudaStreamSynchronize(c->stream);
+    }
+    delete s;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_stats(vb_shuf *s, vb_stats *out)
+{
+    if (!s || !out) return set_err(VB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    cudaSetDevice(s->ctx->device);
+    resolve_timers(s);
+    *out = s->st;
+    return VB_OK;
+}
+
+// per-kernel-class device time (profiling on): klass 0 hash_agg, 1 dict, 2 merge, 3 rp_hist,
+// 4 rp_scan, 5 rp_scatter, 6 misc, 7 join
+extern "C" int32_t vb_shuffle_kernel_time(vb_shuf *s, int32_t klass, double *ms, uint64_t *launches)
+{
+    if (!s || klass < 0 || klass >= K_N) return set_err(VB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    cudaSetDevice(s->ctx->device);
+    resolve_timers(s);
+    if (ms) *ms = s->kms[klass];
+    if (launches) *launches = s->klaunch[klass];
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side pieces of the path
+// ---------------------------------------------------------------------------------------------
+extern "C" uint64_t vb_hash_key(uint64_t key, uint32_t key_width) { return hash_key(key, key_width); }
+
+extern "C" uint32_t vb_get_partition(uint64_t key, uint32_t key_width, uint32_t n_reduce)
+{
+    if (n_reduce == 0) return 0;
+    return (uint32_t)(hash_key(key, key_width) % (uint64_t)n_reduce);
+}
+
+// ParallelCollection::slice (src/rdd/parallel_collection_rdd.rs:116-145): contiguous slices with
+// boundaries floor((s+1)*n/num_slices); one cut per element at most, so n < num_slices yields an
+// empty leading slice and n singletons.
+extern "C" uint64_t vb_slice(uint64_t n, uint64_t num_slices, uint64_t *starts)
+{
+    if (num_slices < 1 || !starts) return 0;
+    uint64_t cut = 0, taken = 0, n_out = 0, first = 0;
+    uint64_t end = ((cut + 1) * n) / num_slices;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (taken >= end) {
+            ++cut;
+            end = ((cut + 1) * n) / num_slices;
+            starts[n_out++] = first;
+            first = i;
+        }
+        ++taken;
+    }
+    starts[n_out++] = first;
+    starts[n_out] = n;
+    return n_out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic input
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t vb_gen_pairs(vb_ctx *c, void *rows_dev, void *keys_dev, void *vals_dev, uint64_t first, uint64_t n,
+                                int32_t mode, uint64_t n_distinct, uint64_t rank_base, uint64_t seed_k, uint64_t seed_v,
+                                double zipf_s)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    if (!rows_dev && !keys_dev) return set_err(VB_ERR_INVALID, "no output buffer");
+    if (mode < GEN_UNIFORM || mode > GEN_UNIQUE) return set_err(VB_ERR_INVALID, "bad generator mode");
+    if (mode != GEN_UNIQUE && n_distinct == 0) return set_err(VB_ERR_INVALID, "n_distinct must be > 0");
+    if (n == 0) return VB_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (mode == GEN_ZIPF && (c->zipf_n != n_distinct || c->zipf_s != zipf_s)) {
+        std::vector<double> cdf(n_distinct);
+        long double h = 0;
+        for (u64 k = 0; k < n_distinct; ++k) { h += 1.0L / powl((long double)(k + 1), (long double)zipf_s); cdf[k] = (double)h; }
+        for (u64 k = 0; k < n_distinct; ++k) cdf[k] = (double)(cdf[k] / (double)h);
+        cdf[n_distinct - 1] = 1.0;
+        if (c->zipf_cdf) cudaFreeAsync(c->zipf_cdf, c->stream);
+        c->zipf_cdf = nullptr;
+        CU(cudaMallocAsync((void **)&c->zipf_cdf, n_distinct * 8, c->pool, c->stream));
+        CU(cudaMemcpyAsync(c->zipf_cdf, cdf.data(), n_distinct * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->zipf_n = n_distinct;
+        c->zipf_s = zipf_s;
+    }
+    u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 16);
+    gen_pairs_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((u64 *)rows_dev, (u64 *)keys_dev, (u64 *)vals_dev, first, n, mode,
+                                                              n_distinct, rank_base, seed_k, seed_v, c->zipf_cdf);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return VB_OK;
+}

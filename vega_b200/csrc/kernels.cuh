@@ -1,0 +1,674 @@
+// kernels.cuh — hand-written sm_100a kernels of the shuffle + aggregation path.
+//
+//   hash_agg_kernel   map-side combine (dependency.rs:191-210) and reduce-side merge
+//                     (shuffled_rdd.rs:154-164) as one streaming pass into an L2-resident
+//                     open-addressing table: 128-bit evict-first loads, one probe + one RED per row.
+//                     OPK_DICT variant builds the key dictionary for group_by_key / cogroup.
+//   rp_hist / rp_scatter   one stable radix pass (multisplit by hash(K) % nparts, LSD sort digits):
+//                     warp match-any ranking, shared-memory staged tiles, coalesced run writes.
+//   scan kernels, CSR boundary, join probe/expand, generators.
+//
+// Integer / indexing work: HBM- and L2-bound, no tensor cores by design.
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+
+// ---------------------------------------------------------------------------------------------
+// Hash table
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) Slot {
+    u64 key;
+    u64 acc;
+};
+constexpr u64 EMPTY_KEY = ~0ull;
+// tab[cap] is the dedicated home of a real key equal to EMPTY_KEY: .key = 1 when present.
+
+struct TableCtl {
+    u32 abort;        // set by the kernel: table too full / probe sequence too long → host restarts
+    u32 pad;
+    unsigned long long n_inserted;
+};
+
+enum : int { IN_AOS = 0, IN_SOA = 1, IN_TABLE = 2 };
+enum : int { OPK_ADD_U64 = 0, OPK_ADD_F64 = 1, OPK_MIN_U64 = 2, OPK_MAX_U64 = 3, OPK_COUNT = 4, OPK_DICT = 5 };
+
+VB_HD u64 op_identity(int opk) { return opk == OPK_MIN_U64 ? ~0ull : 0ull; }
+
+template <int OPK>
+VB_D void op_red(u64 *acc, u64 v)
+{
+    if (OPK == OPK_ADD_U64) atomicAdd((unsigned long long *)acc, (unsigned long long)v);
+    else if (OPK == OPK_COUNT) atomicAdd((unsigned long long *)acc, 1ull);
+    else if (OPK == OPK_ADD_F64) atomicAdd((double *)acc, __longlong_as_double((long long)v));
+    else if (OPK == OPK_MIN_U64) atomicMin((unsigned long long *)acc, (unsigned long long)v);
+    else if (OPK == OPK_MAX_U64) atomicMax((unsigned long long *)acc, (unsigned long long)v);
+}
+
+__global__ void table_init_kernel(Slot *tab, u64 cap, u64 identity)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i <= cap; i += stride) {
+        Slot s;
+        s.key = (i == cap) ? 0ull : EMPTY_KEY;
+        s.acc = identity;
+        tab[i] = s;
+    }
+}
+
+constexpr int HA_THREADS = 256;
+constexpr int HA_ROWS = 4;
+constexpr int HA_TILE = HA_THREADS * HA_ROWS;
+constexpr u32 HA_MAX_PROBE = 512;
+
+// Probe/insert `key`; on success returns the slot index.  `inserted` counts new keys.
+template <int OPK>
+VB_D bool table_upsert(Slot *tab, u64 mask, u32 shift, u64 key, u64 v, u32 &slot_idx, u32 &inserted)
+{
+    u64 s = slot_hash(key) >> shift;
+#pragma unroll 1
+    for (u32 probe = 0; probe < HA_MAX_PROBE; ++probe) {
+        u64 k = ld_cg_u64(&tab[s].key);
+        if (k == EMPTY_KEY) {
+            k = atomicCAS((unsigned long long *)&tab[s].key, (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+            if (k == EMPTY_KEY) { ++inserted; k = key; }
+        }
+        if (k == key) {
+            op_red<OPK>(&tab[s].acc, v);
+            slot_idx = (u32)s;
+            return true;
+        }
+        s = (s + 1) & mask;
+    }
+    return false;
+}
+
+// One pass over n rows.  IN_AOS: a = rows (16 B each).  IN_SOA: a = keys, b = vals (b may be
+// NULL for COUNT/DICT).  IN_TABLE: a = source Slot table of n-1 slots + the special slot.
+// TX: order-preserving value transform applied on load (MIN/MAX over i64/f64).
+template <int IN, int OPK, int TX>
+__global__ void __launch_bounds__(HA_THREADS)
+hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Slot *tab, u32 log_cap, TableCtl *ctl,
+                u64 max_inserts, u32 *__restrict__ slot_out)
+{
+    __shared__ u32 s_inserts;
+    __shared__ u32 s_abort;
+    const u32 tid = threadIdx.x;
+    if (tid == 0) { s_inserts = 0; s_abort = 0; }
+    __syncthreads();
+    const u64 pol = policy_evict_first();
+    const u64 cap = 1ull << log_cap;
+    const u64 mask = cap - 1;
+    const u32 shift = 64 - log_cap;
+    const u64 n_tiles = (n + HA_TILE - 1) / HA_TILE;
+    u32 my_inserts = 0;
+    u32 iter = 0;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        const u64 base = tile * HA_TILE;
+        u64 k[HA_ROWS], v[HA_ROWS];
+        bool ok[HA_ROWS];
+#pragma unroll
+        for (int j = 0; j < HA_ROWS; ++j) {
+            const u64 idx = base + (u64)j * HA_THREADS + tid;
+            ok[j] = idx < n;
+            k[j] = 0; v[j] = 0;
+            if (ok[j]) {
+                if (IN == IN_AOS) {
+                    ulonglong2 r = ld_stream_u64x2(a + 2 * idx, pol);
+                    k[j] = r.x; v[j] = r.y;
+                } else if (IN == IN_SOA) {
+                    k[j] = ld_stream_u64(a + idx, pol);
+                    if (OPK != OPK_COUNT && OPK != OPK_DICT) v[j] = ld_stream_u64(b + idx, pol);
+                } else {
+                    ulonglong2 r = ld_stream_u64x2(a + 2 * idx, pol);
+                    k[j] = r.x; v[j] = r.y;
+                    if (idx == n - 1) { ok[j] = (r.x == 1ull); k[j] = EMPTY_KEY; }   // special slot
+                    else if (r.x == EMPTY_KEY) ok[j] = false;                        // unoccupied
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HA_ROWS; ++j) {
+            if (!ok[j]) continue;
+            const u64 idx = base + (u64)j * HA_THREADS + tid;
+            const u64 val = (TX == TX_NONE) ? v[j] : tx_fwd(v[j], TX);
+            u32 slot = 0;
+            if (k[j] == EMPTY_KEY) {
+                tab[cap].key = 1ull;
+                op_red<OPK>(&tab[cap].acc, val);
+                slot = (u32)cap;
+            } else if (!table_upsert<OPK>(tab, mask, shift, k[j], val, slot, my_inserts)) {
+                atomicExch(&ctl->abort, 1u);
+            }
+            if (OPK == OPK_DICT) st_stream_u32(slot_out + idx, slot);
+        }
+        if ((iter & 15u) == 15u) {   // periodic load-factor check; iter is CTA-uniform
+            u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
+            my_inserts = 0;
+            if ((tid & 31u) == 0 && w) atomicAdd(&s_inserts, w);
+            __syncthreads();
+            if (tid == 0) {
+                u32 c = s_inserts;
+                s_inserts = 0;
+                u64 tot = atomicAdd(&ctl->n_inserted, (unsigned long long)c) + c;
+                u32 ab = ld_volatile_u32(&ctl->abort);
+                if (tot > max_inserts) { ab = 1; atomicExch(&ctl->abort, 1u); }
+                s_abort = ab;
+            }
+            __syncthreads();
+            if (s_abort) return;
+        }
+    }
+    u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
+    if ((tid & 31u) == 0 && w) atomicAdd(&s_inserts, w);
+    __syncthreads();
+    if (tid == 0 && s_inserts) atomicAdd(&ctl->n_inserted, (unsigned long long)s_inserts);
+}
+
+// Read-only lookup used by the join: slot index of `key`, or 0xFFFFFFFF.
+VB_D u32 table_find(const Slot *tab, u32 log_cap, u64 key)
+{
+    const u64 cap = 1ull << log_cap, mask = cap - 1;
+    if (key == EMPTY_KEY) return tab[cap].key == 1ull ? (u32)cap : 0xFFFFFFFFu;
+    u64 s = slot_hash(key) >> (64 - log_cap);
+    for (u32 probe = 0; probe <= HA_MAX_PROBE; ++probe) {
+        u64 k = tab[s].key;
+        if (k == key) return (u32)s;
+        if (k == EMPTY_KEY) return 0xFFFFFFFFu;
+        s = (s + 1) & mask;
+    }
+    return 0xFFFFFFFFu;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Radix pass (stable multisplit / one LSD digit)
+// ---------------------------------------------------------------------------------------------
+constexpr int RP_THREADS = 256;
+constexpr int RP_WARPS = RP_THREADS / 32;
+constexpr int RP_ITEMS = 16;
+constexpr int RP_TILE = RP_THREADS * RP_ITEMS;   // 4096 rows
+constexpr int RP_NB = 256;                       // bins per pass; bin RP_NB = "invalid, drop"
+
+enum : int { LD_SOA64 = 0, LD_AOS64 = 1, LD_KEY32_VAL_SOA = 2, LD_KEY32_VAL_AOS = 3, LD_TABLE_KV = 4, LD_TABLE_KI = 5 };
+
+// Where a pass reads its rows from.  One struct, run-time mode (CTA-uniform branch).
+struct Loader {
+    int mode;
+    const void *keys;   // u64* / u32* / rows (AoS) / Slot*
+    const void *vals;   // u64* or AoS rows for LD_KEY32_VAL_AOS
+    u64 cap;            // table modes: number of regular slots (row `cap` is the special slot)
+};
+
+template <typename KeyT>
+VB_D bool rp_load(const Loader &ld, u64 i, KeyT &key, u64 &val, u64 pol)
+{
+    switch (ld.mode) {
+    case LD_SOA64:
+        key = (KeyT)ld_stream_u64((const u64 *)ld.keys + i, pol);
+        val = ld.vals ? ld_stream_u64((const u64 *)ld.vals + i, pol) : 0ull;
+        return true;
+    case LD_AOS64: {
+        ulonglong2 r = ld_stream_u64x2((const u64 *)ld.keys + 2 * i, pol);
+        key = (KeyT)r.x; val = r.y;
+        return true;
+    }
+    case LD_KEY32_VAL_SOA:
+        key = (KeyT)ld_stream_u32((const u32 *)ld.keys + i, pol);
+        val = ld.vals ? ld_stream_u64((const u64 *)ld.vals + i, pol) : 0ull;
+        return true;
+    case LD_KEY32_VAL_AOS:
+        key = (KeyT)ld_stream_u32((const u32 *)ld.keys + i, pol);
+        val = ld_stream_u64((const u64 *)ld.vals + 2 * i + 1, pol);
+        return true;
+    case LD_TABLE_KV:
+    case LD_TABLE_KI: {
+        const Slot *t = (const Slot *)ld.keys;
+        ulonglong2 r = ld_stream_u64x2(&t[i], pol);
+        val = (ld.mode == LD_TABLE_KI) ? i : r.y;
+        if (i == ld.cap) { key = (KeyT)EMPTY_KEY; return r.x == 1ull; }
+        key = (KeyT)r.x;
+        return r.x != EMPTY_KEY;
+    }
+    }
+    return false;
+}
+
+enum : int { DG_BITS = 0, DG_BUCKET = 1, DG_DEST = 2, DG_RANGE = 3 };
+
+// Which bin a key goes to.  DG_BITS: radix digit of the (order-transformed) key.  DG_BUCKET:
+// digit of HashPartitioner::get_partition(key).  DG_DEST: owning rank = partition % world.
+struct Digit {
+    int mode;
+    u32 shift, mask;
+    int tx;
+    u32 key_width;
+    FastMod fm;        // % n_reduce
+    FastMod fm_world;  // % world
+};
+
+template <typename KeyT>
+VB_D u32 rp_digit(const Digit &dg, KeyT key)
+{
+    if (dg.mode == DG_BITS) {
+        u64 k = (sizeof(KeyT) == 8) ? tx_fwd((u64)key, dg.tx) : (u64)key;
+        return (u32)(k >> dg.shift) & dg.mask;
+    }
+    u32 b = get_partition((u64)key, dg.key_width, dg.fm);
+    if (dg.mode == DG_DEST) return fastmod(b, dg.fm_world);
+    return (b >> dg.shift) & dg.mask;
+}
+
+// part p covers rows [p*rows_per_part, min(n, (p+1)*rows_per_part)); hist[d*num_parts + p]
+template <typename KeyT>
+__global__ void __launch_bounds__(RP_THREADS)
+rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ hist, u32 num_parts)
+{
+    __shared__ u32 cnt[RP_WARPS][RP_NB + 1];
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    for (u32 d = tid; d < RP_WARPS * (RP_NB + 1); d += RP_THREADS) (&cnt[0][0])[d] = 0;
+    __syncthreads();
+    const u64 pol = policy_evict_first();
+    const u32 part = blockIdx.x;
+    const u64 begin = (u64)part * rows_per_part;
+    const u64 end = min(n, begin + rows_per_part);
+    for (u64 t0 = begin; t0 < end; t0 += RP_TILE) {
+#pragma unroll 4
+        for (int i = 0; i < RP_ITEMS; ++i) {
+            const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)i * 32 + lane;
+            u32 d = RP_NB;
+            if (idx < end) {
+                KeyT key; u64 val;
+                if (rp_load<KeyT>(ld, idx, key, val, pol)) d = rp_digit<KeyT>(dg, key);
+            }
+            const u32 peers = __match_any_sync(0xffffffffu, d);
+            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (u32 d = tid; d < RP_NB; d += RP_THREADS) {
+        u32 s = 0;
+#pragma unroll
+        for (int w = 0; w < RP_WARPS; ++w) s += cnt[w][d];
+        hist[(u64)d * num_parts + part] = s;
+    }
+}
+
+// Exclusive scan of hist[0 .. len) in place (single CTA); total written to hist[len].
+__global__ void __launch_bounds__(1024) rp_scan_kernel(u32 *hist, u32 len)
+{
+    __shared__ u32 warp_sums[32];
+    __shared__ u32 s_total;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 per = (len + 1023u) / 1024u;
+    const u32 lo = min(len, tid * per), hi = min(len, lo + per);
+    u32 s = 0;
+    for (u32 i = lo; i < hi; ++i) s += hist[i];
+    u32 incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (u32)off) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 ws = warp_sums[lane];
+        u32 wi = ws;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= (u32)off) wi += t;
+        }
+        warp_sums[lane] = wi - ws;
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    u32 run = warp_sums[warp] + (incl - s);
+    for (u32 i = lo; i < hi; ++i) {
+        u32 c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+    if (tid == 0) hist[len] = s_total;
+}
+
+template <typename KeyT, bool HAS_VAL>
+__global__ void __launch_bounds__(RP_THREADS)
+rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
+                  KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *stage_vals = (u64 *)smem_raw;                                       // [RP_TILE] if HAS_VAL
+    KeyT *stage_keys = (KeyT *)(smem_raw + (HAS_VAL ? RP_TILE * 8 : 0));     // [RP_TILE]
+    unsigned char *stage_dig = (unsigned char *)(stage_keys + RP_TILE);      // [RP_TILE]
+    __shared__ u32 cnt[RP_WARPS][RP_NB + 1];
+    __shared__ u32 tot[RP_NB + 1];
+    __shared__ u32 dbase[RP_NB + 2];
+    __shared__ u32 gbase[RP_NB];
+    __shared__ u32 run_off[RP_NB];
+
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const u32 lt = lanemask_lt();
+    const u64 pol = policy_evict_first();
+    const u32 part = blockIdx.x;
+    const u64 begin = (u64)part * rows_per_part;
+    const u64 end = min(n, begin + rows_per_part);
+    for (u32 d = tid; d < RP_NB; d += RP_THREADS) run_off[d] = part_off[(u64)d * num_parts + part];
+
+    for (u64 t0 = begin; t0 < end; t0 += RP_TILE) {
+        for (u32 d = tid; d < RP_WARPS * (RP_NB + 1); d += RP_THREADS) (&cnt[0][0])[d] = 0;
+        __syncthreads();   // also orders run_off init / previous tile's smem reads
+
+        KeyT key[RP_ITEMS];
+        u64 val[RP_ITEMS];
+        unsigned short dig[RP_ITEMS], rank[RP_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RP_ITEMS; ++i) {
+            const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)i * 32 + lane;
+            u32 d = RP_NB;
+            key[i] = 0; val[i] = 0;
+            if (idx < end) {
+                if (rp_load<KeyT>(ld, idx, key[i], val[i], pol)) d = rp_digit<KeyT>(dg, key[i]);
+            }
+            dig[i] = (unsigned short)d;
+        }
+#pragma unroll
+        for (int i = 0; i < RP_ITEMS; ++i) {
+            const u32 d = dig[i];
+            const u32 peers = __match_any_sync(0xffffffffu, d);
+            const u32 base = cnt[warp][d];
+            __syncwarp();
+            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = base + __popc(peers);
+            __syncwarp();
+            rank[i] = (unsigned short)(base + __popc(peers & lt));
+        }
+        __syncthreads();
+        // per digit: exclusive scan over warps, total
+        for (u32 d = tid; d <= RP_NB; d += RP_THREADS) {
+            u32 s = 0;
+#pragma unroll
+            for (int w = 0; w < RP_WARPS; ++w) { u32 c = cnt[w][d]; cnt[w][d] = s; s += c; }
+            tot[d] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {   // exclusive scan of tot[0..RP_NB] → dbase
+            constexpr int PER = (RP_NB + 1 + 31) / 32;
+            u32 loc[PER];
+            u32 s = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                u32 e = lane * PER + j;
+                u32 c = (e <= RP_NB) ? tot[e] : 0u;
+                loc[j] = s; s += c;
+            }
+            u32 incl = s;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= (u32)off) incl += t;
+            }
+            const u32 excl = incl - s;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                u32 e = lane * PER + j;
+                if (e <= RP_NB) dbase[e] = excl + loc[j];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RP_ITEMS; ++i) {
+            const u32 d = dig[i];
+            const u32 pos = dbase[d] + cnt[warp][d] + rank[i];
+            stage_keys[pos] = key[i];
+            if (HAS_VAL) stage_vals[pos] = val[i];
+            stage_dig[pos] = (unsigned char)d;   // d == RP_NB wraps to 0 but lives past n_valid
+        }
+        for (u32 d = tid; d < RP_NB; d += RP_THREADS) gbase[d] = run_off[d] - dbase[d];
+        __syncthreads();
+        const u32 n_valid = dbase[RP_NB];
+        for (u32 p = tid; p < n_valid; p += RP_THREADS) {
+            const u32 d = stage_dig[p];
+            const u32 o = gbase[d] + p;
+            out_keys[o] = stage_keys[p];
+            if (HAS_VAL) out_vals[o] = stage_vals[p];
+        }
+        __syncthreads();
+        for (u32 d = tid; d < RP_NB; d += RP_THREADS) run_off[d] += tot[d];
+        // next iteration's first __syncthreads orders this against its readers
+    }
+}
+
+template <typename KeyT, bool HAS_VAL>
+constexpr size_t rp_scatter_smem() { return (size_t)RP_TILE * ((HAS_VAL ? 8 : 0) + sizeof(KeyT) + 1); }
+
+// ---------------------------------------------------------------------------------------------
+// Generic multi-block exclusive scan (u64), chunk = 4096 elements per CTA
+// ---------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 16;
+constexpr int SC_CHUNK = SC_THREADS * SC_ITEMS;
+
+VB_D u64 block_exclusive_scan_u64(u64 v, u64 *total, u64 *warp_sums /*[8]*/)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    u64 incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (u32)off) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    u64 wbase = 0, tsum = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; ++w) {
+        u64 x = warp_sums[w];
+        if ((u32)w < warp) wbase += x;
+        tsum += x;
+    }
+    *total = tsum;
+    __syncthreads();
+    return wbase + incl - v;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const u64 *__restrict__ in, u64 n, u64 *__restrict__ sums)
+{
+    __shared__ u64 ws[SC_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * SC_CHUNK;
+    u64 s = 0;
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        u64 idx = base + (u64)i * SC_THREADS + threadIdx.x;
+        if (idx < n) s += in[idx];
+    }
+    u64 tot;
+    block_exclusive_scan_u64(s, &tot, ws);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+// out[i] = offsets[block] + exclusive prefix within the chunk.  offsets may be NULL (single chunk).
+// If total_out != NULL the last block writes the grand total there.
+__global__ void __launch_bounds__(SC_THREADS)
+scan_apply_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, const u64 *__restrict__ offsets, u64 *total_out)
+{
+    __shared__ u64 ws[SC_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * SC_CHUNK + (u64)threadIdx.x * SC_ITEMS;
+    u64 v[SC_ITEMS];
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0ull;
+        s += v[i];
+    }
+    u64 tot;
+    u64 run = block_exclusive_scan_u64(s, &tot, ws) + (offsets ? offsets[blockIdx.x] : 0ull);
+    const u64 carry_in = offsets ? offsets[blockIdx.x] : 0ull;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = carry_in + tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// group_by_key helpers
+// ---------------------------------------------------------------------------------------------
+// dense_of_slot[cslot[j]] = j   (cslot holds slot indices as u64 payloads of the bucket multisplit)
+__global__ void scatter_dense_kernel(const u64 *__restrict__ cslot, u32 n, u32 *__restrict__ dense_of_slot)
+{
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dense_of_slot[cslot[j]] = j;
+}
+
+// ids[i] = dense_of_slot[ids[i]] in place (the 4 MB–64 MB dense_of_slot array is L2-resident)
+__global__ void translate_ids_kernel(u32 *__restrict__ ids, u64 n, const u32 *__restrict__ dense_of_slot)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) ids[i] = dense_of_slot[ids[i]];
+}
+
+// CSR offsets from sorted dense ids: offsets[id] = first row of id; offsets[n_ids] = n.
+__global__ void csr_bounds_kernel(const u32 *__restrict__ ids, u64 n, u64 *__restrict__ offsets, u64 n_ids)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    if (i == 0) offsets[n_ids] = n;
+    for (; i < n; i += stride) {
+        u32 id = ids[i];
+        if (i == 0 || ids[i - 1] != id) offsets[id] = i;
+    }
+}
+
+// out[i] = tx_inv(in[i])
+__global__ void tx_inv_kernel(u64 *__restrict__ v, u64 n, int tx)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = tx_inv(v[i], tx);
+}
+
+// de-interleave AoS rows into SoA (gather of map partitions that are not contiguous)
+__global__ void aos_to_soa_kernel(const u64 *__restrict__ rows, u64 n, u64 *__restrict__ keys, u64 *__restrict__ vals)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 pol = policy_evict_first();
+    for (; i < n; i += stride) {
+        ulonglong2 r = ld_stream_u64x2(rows + 2 * i, pol);
+        keys[i] = r.x;
+        vals[i] = r.y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// join (CoGroupedRdd::compute + cross product)
+// ---------------------------------------------------------------------------------------------
+// For left keys [lb, le): find the key in the right shuffle's dictionary; cnt = lenL * lenR.
+__global__ void join_probe_kernel(const u64 *__restrict__ lkeys, const u64 *__restrict__ loffs, u32 lb, u32 le,
+                                  const Slot *__restrict__ rtab, u32 r_log_cap, const u32 *__restrict__ r_dense,
+                                  const u64 *__restrict__ roffs, u64 *__restrict__ cnt, u32 *__restrict__ match)
+{
+    u32 j = lb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= le) return;
+    u64 key = lkeys[j];
+    u32 s = table_find(rtab, r_log_cap, key);
+    u64 c = 0;
+    u32 m = 0xFFFFFFFFu;
+    if (s != 0xFFFFFFFFu) {
+        m = r_dense[s];
+        c = (loffs[j + 1] - loffs[j]) * (roffs[m + 1] - roffs[m]);
+    }
+    cnt[j - lb] = c;
+    match[j - lb] = m;
+}
+
+// One thread per output row: binary-search the owning left key, then (v, w) = divmod.
+__global__ void join_expand_kernel(const u64 *__restrict__ pos /*[nl] exclusive*/, u32 nl, u64 total,
+                                   const u64 *__restrict__ lkeys, const u64 *__restrict__ loffs, const u64 *__restrict__ lvals,
+                                   u32 lb, const u32 *__restrict__ match, const u64 *__restrict__ roffs,
+                                   const u64 *__restrict__ rvals, u64 *__restrict__ out_k, u64 *__restrict__ out_v,
+                                   u64 *__restrict__ out_w)
+{
+    u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; o < total; o += stride) {
+        u32 lo = 0, hi = nl;   // largest j with pos[j] <= o  (keys with cnt 0 share pos with the next)
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (pos[mid] <= o) lo = mid; else hi = mid;
+        }
+        const u32 j = lo;
+        const u32 m = match[j];
+        const u64 local = o - pos[j];
+        const u64 lenr = roffs[m + 1] - roffs[m];
+        const u64 vi = local / lenr, wi = local - vi * lenr;
+        out_k[o] = lkeys[lb + j];
+        out_v[o] = lvals[loffs[lb + j] + vi];
+        out_w[o] = rvals[roffs[m] + wi];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sort_by_key partition cuts: start of partition p = floor(p*n/R) moved past equal keys
+// ---------------------------------------------------------------------------------------------
+__global__ void sort_cuts_kernel(const u64 *__restrict__ keys, u64 n, u32 n_parts, u64 *__restrict__ starts)
+{
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_parts) return;
+    if (p == 0) { starts[0] = 0; return; }
+    if (p == n_parts) { starts[p] = n; return; }
+    u64 c = ((u64)p * n) / n_parts;   // n < 2^32 and p < 2^32: no overflow
+    if (c > 0 && c < n && keys[c] == keys[c - 1]) {   // upper bound of keys[c-1] in [c, n)
+        const u64 k = keys[c - 1];
+        u64 lo = c, hi = n;
+        while (lo < hi) {
+            u64 mid = lo + ((hi - lo) >> 1);
+            if (keys[mid] == k) lo = mid + 1; else hi = mid;
+        }
+        c = lo;
+    }
+    starts[p] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic input; must match oracle/vega_oracle.c:vo_gen_uniform bit for bit
+// ---------------------------------------------------------------------------------------------
+enum : int { GEN_UNIFORM = 0, GEN_ZIPF = 1, GEN_UNIQUE = 2 };
+
+__global__ void gen_pairs_kernel(u64 *__restrict__ rows, u64 *__restrict__ keys, u64 *__restrict__ vals, u64 first, u64 n,
+                                 int mode, u64 n_distinct, u64 rank_base, u64 seed_k, u64 seed_v,
+                                 const double *__restrict__ zipf_cdf)
+{
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const u64 i = first + t;
+        u64 rank;
+        if (mode == GEN_UNIQUE) {
+            rank = rank_base + i;
+        } else if (mode == GEN_ZIPF) {
+            const double u = (double)(splitmix64(seed_k + i) >> 11) * (1.0 / 9007199254740992.0);
+            u64 lo = 0, hi = n_distinct - 1;     // first index with cdf[idx] >= u
+            while (lo < hi) {
+                u64 mid = (lo + hi) >> 1;
+                if (zipf_cdf[mid] >= u) hi = mid; else lo = mid + 1;
+            }
+            rank = lo;
+        } else {
+            rank = splitmix64(seed_k + i) % n_distinct;
+        }
+        const u64 k = splitmix64(rank ^ 0xA5A5A5A5A5A5A5A5ull);
+        const u64 v = splitmix64(seed_v + i) & 0xFFFFFull;
+        if (rows) {
+            ulonglong2 r; r.x = k; r.y = v;
+            *reinterpret_cast<ulonglong2 *>(rows + 2 * t) = r;
+        } else {
+            keys[t] = k;
+            if (vals) vals[t] = v;
+        }
+    }
+}
+
+}  // namespace vb

@@ -1,0 +1,121 @@
+"""One-process-per-GPU shuffle: the data plane between map side and reduce side.
+
+The reference moves shuffle blocks with one HTTP GET per (map, reduce) pair
+(src/shuffle/shuffle_fetcher.rs:61-86 → src/shuffle/shuffle_manager.rs:176-251).  Here every
+rank packs its map output by destination rank on the device (vb_shuffle_export_prepare: a
+stable multisplit, so rows stay in map-id / encounter order), the ranks swap a world×world
+count vector, and ONE all-to-all-v per column (torch.distributed → NCCL grouped send/recv over
+NVLink/NVSwitch; gloo on CPU for the host-logic tests) delivers them.  Reduce partition r is
+owned by rank r % world; map partitions are assigned to ranks in contiguous blocks so that the
+source-rank-major receive order IS map-id order (group value order).
+
+reduce ops exchange *combined* rows (≤ distinct keys per rank — map-side combine,
+src/dependency.rs:203-209), group ops exchange raw rows.
+
+The engine is pluggable only so that the exchange logic can be tested on CPU with gloo
+(tests/ plug in an oracle-backed stand-in); the product engine is CudaEngine.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+from .rdd import Shuffle, _Col
+
+
+def map_block(rank, world, n_map):
+    """Contiguous block of map partitions owned by `rank`: [lo, hi)."""
+    return (rank * n_map) // world, ((rank + 1) * n_map) // world
+
+
+class _DevArray:
+    """Zero-copy view of a library-owned device buffer for torch.as_tensor."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class CudaEngine:
+    """libvega_b200 on this rank's GPU."""
+
+    def __init__(self, sc):
+        self.sc = sc
+
+    def create(self, n_map, n_reduce, kcode, vcode, agg, rank, world, key_width=8, hint=0):
+        return Shuffle(self.sc, n_map, n_reduce, kcode, vcode, agg, key_width=key_width, hint=hint, rank=rank, world=world)
+
+    def map(self, sh, map_id, keys, vals):
+        k = keys if isinstance(keys, _Col) else _Col(keys, allow_rows=True)
+        v = None if vals is None else (vals if isinstance(vals, _Col) else _Col(vals))
+        sh.map(map_id, k, v, 0, k.n)
+
+    def export(self, sh, world):
+        import torch
+        counts = (ctypes.c_uint64 * world)()
+        L.check(sh._lib.vb_shuffle_export_prepare(sh._h, counts))
+        counts = [int(c) for c in counts]
+        kp, vp = ctypes.c_void_p(), ctypes.c_void_p()
+        L.check(sh._lib.vb_shuffle_export_buffers(sh._h, ctypes.byref(kp), ctypes.byref(vp)))
+        n = sum(counts)
+        dev = f"cuda:{sh._lib.vb_ctx_device(self.sc._h)}"
+        if n == 0:
+            e = torch.empty(0, dtype=torch.int64, device=dev)
+            return counts, e, e.clone()
+        keys = torch.as_tensor(_DevArray(kp.value, n), device=dev)
+        vals = torch.as_tensor(_DevArray(vp.value, n), device=dev)
+        return counts, keys, vals
+
+    def import_(self, sh, keys, vals, counts):
+        sh._imported = (keys, vals)            # keep the tensors alive until seal
+        c = (ctypes.c_uint64 * len(counts))(*counts)
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
+        L.check(sh._lib.vb_shuffle_import(sh._h, p(keys), p(vals), c))
+
+    def seal(self, sh):
+        sh.seal()
+        sh._imported = None
+
+    def reduce(self, sh, r):
+        return sh.reduce(r)
+
+
+def all_to_all_v(send_keys, send_vals, send_counts, group=None):
+    """The shuffle's single exchange step: counts, then keys and values, each one
+    all_to_all_single.  Returns (recv_keys, recv_vals, recv_counts), source-rank major."""
+    import torch
+    import torch.distributed as dist
+    dev = send_keys.device
+    cin = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    cout = torch.empty_like(cin)
+    dist.all_to_all_single(cout, cin, group=group)
+    recv_counts = [int(x) for x in cout.tolist()]
+    rk = torch.empty(sum(recv_counts), dtype=send_keys.dtype, device=dev)
+    rv = torch.empty(sum(recv_counts), dtype=send_vals.dtype, device=dev)
+    dist.all_to_all_single(rk, send_keys, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+    dist.all_to_all_single(rv, send_vals, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+    return rk, rv, recv_counts
+
+
+def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, world, group=None, key_width=8, hint=0,
+                stats=None):
+    """Map side on this rank's partitions → exchange → reduce side for the partitions this rank owns.
+
+    local_maps: [(map_id, keys, vals_or_None)], ascending map ids from map_block(rank, world, n_map).
+    Returns the sealed engine handle; engine.reduce(h, r) is non-empty only for r % world == rank.
+    """
+    sh = engine.create(n_map, n_reduce, kcode, vcode, agg, rank, world, key_width=key_width, hint=hint)
+    for map_id, keys, vals in local_maps:
+        engine.map(sh, map_id, keys, vals)
+    if world > 1:
+        counts, sk, sv = engine.export(sh, world)
+        rk, rv, rcounts = all_to_all_v(sk, sv, counts, group)
+        if stats is not None:
+            stats["sent_rows"] = sum(counts) - counts[rank]
+            stats["recv_rows"] = sum(rcounts) - rcounts[rank]
+        engine.import_(sh, rk, rv, rcounts)
+    engine.seal(sh)
+    return sh
+
+
+def owned_partitions(rank, world, n_reduce):
+    return [r for r in range(n_reduce) if r % world == rank]
