@@ -1,0 +1,39 @@
+//! vega_b200_sys.rs — `extern "C"` declarations of libvega_b200.so for vega (Rust).
+//!
+//! SOURCE ONLY: this image has no rustc/cargo (and vega needs nightly-2020-05-31 + capnpc), so
+//! this file has never been compiled.  It is the binding a vega maintainer would add as
+//! `src/gpu/sys.rs`; see INTEGRATION.md for the four call-site patches that use it.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)] pub struct vb_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct vb_shuf { _p: [u8; 0] }
+
+pub const VB_OK: i32 = 0;
+pub const VB_U64: i32 = 0; pub const VB_I64: i32 = 1; pub const VB_F64: i32 = 2;
+pub const VB_AGG_GROUP: i32 = 0; pub const VB_AGG_SUM: i32 = 1; pub const VB_AGG_MIN: i32 = 2;
+pub const VB_AGG_MAX: i32 = 3; pub const VB_AGG_COUNT: i32 = 4; pub const VB_AGG_COGROUP: i32 = 5;
+pub const VB_PART_HASH_METRO64: i32 = 0;
+pub const VB_HOST: i32 = 0;
+
+#[link(name = "vega_b200")]
+extern "C" {
+    pub fn vb_ctx_create(device_id: i32, out: *mut *mut vb_ctx) -> i32;
+    pub fn vb_ctx_destroy(ctx: *mut vb_ctx) -> i32;
+    pub fn vb_shuffle_create(ctx: *mut vb_ctx, shuffle_id: u64, n_map: u32, n_reduce: u32, key_dtype: i32,
+                             val_dtype: i32, agg: i32, part: i32, out: *mut *mut vb_shuf) -> i32;
+    pub fn vb_shuffle_set_key_width(s: *mut vb_shuf, bytes: u32) -> i32;
+    pub fn vb_shuffle_map_aos(s: *mut vb_shuf, map_id: u32, rows: *const c_void, n_rows: u64, src_loc: i32) -> i32;
+    pub fn vb_shuffle_map_soa(s: *mut vb_shuf, map_id: u32, keys: *const c_void, vals: *const c_void,
+                              n_rows: u64, src_loc: i32) -> i32;
+    pub fn vb_shuffle_seal(s: *mut vb_shuf) -> i32;
+    pub fn vb_shuffle_reduce_size(s: *mut vb_shuf, reduce_id: u32, n_keys: *mut u64, n_vals: *mut u64) -> i32;
+    pub fn vb_shuffle_reduce(s: *mut vb_shuf, reduce_id: u32, out_keys: *mut c_void, out_combined: *mut c_void,
+                             out_offsets: *mut u64, out_vals: *mut c_void, dst_loc: i32) -> i32;
+    pub fn vb_join_size(left: *mut vb_shuf, right: *mut vb_shuf, reduce_id: u32, n_out: *mut u64) -> i32;
+    pub fn vb_join(left: *mut vb_shuf, right: *mut vb_shuf, reduce_id: u32, out_k: *mut c_void, out_v: *mut c_void,
+                   out_w: *mut c_void, dst_loc: i32) -> i32;
+    pub fn vb_shuffle_free(s: *mut vb_shuf) -> i32;
+    pub fn vb_last_error() -> *const c_char;
+    pub fn vb_get_partition(key: u64, key_width: u32, n_reduce: u32) -> u32;
+}

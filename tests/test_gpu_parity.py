@@ -168,11 +168,12 @@ def test_empty_and_tiny_inputs(sc):
 
 
 def test_table_growth_all_distinct(sc):
-    # 3M distinct keys force the 2^21-slot first table to restart larger
+    # a (deliberately wrong) hint of 1000 distinct keys sizes the first table at 2^11 slots:
+    # 3M distinct keys must overflow it and restart with larger tables until they fit
     n = 3_000_000
     keys = (np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
     vals = np.ones(n, dtype=np.uint64)
-    rdd = sc.parallelize((keys, vals), 2).reduce_by_key("sum", 4)
+    rdd = sc.parallelize((keys, vals), 2).reduce_by_key("sum", 4, hint=1000)
     k, c = rdd.collect()
     assert len(k) == n and (c == 1).all() and len(np.unique(k)) == n
     assert rdd.stats()["table_restarts"] >= 1
@@ -180,6 +181,9 @@ def test_table_growth_all_distinct(sc):
         kk, _ = rdd.compute(r)
         sample = kk[:: max(1, len(kk) // 50)]
         assert all(O.get_partition(int(x), 4) == r for x in sample)
+    # same through the dictionary of group_by_key
+    g = sc.parallelize((keys[:500_000], vals[:500_000]), 3).group_by_key(2).collect()
+    assert len(g) == 500_000 and (np.diff(g.offsets.astype(np.int64)) == 1).all()
 
 
 @pytest.mark.parametrize("na,nb,R,nkeys", [(20_000, 30_000, 4, 3000), (5000, 10, 3, 50), (1000, 1000, 300, 2000)])
