@@ -196,7 +196,7 @@ struct MapOut {
     bool present = false;
     u64 n_rows = 0;
     // reduce ops: the combined table of this map task (== SHUFFLE_CACHE[(sid, map, *)])
-    Slot *table = nullptr;
+    void *table = nullptr;      // table_at(table, log_cap)
     u32 log_cap = 0;
     u64 n_inserted = 0;
     // group/sort ops: the rows (device), AoS or SoA
@@ -243,7 +243,7 @@ struct vb_shuf {
     u64 *res_keys = nullptr, *res_comb = nullptr, *res_offs = nullptr, *res_vals = nullptr;
     std::vector<u64> bucket_off;   // n_reduce + 1 (key index)
     std::vector<u64> val_off;      // n_reduce + 1 (value index; group ops)
-    Slot *dict = nullptr;          // group ops: key → slot, kept for joins
+    void *dict = nullptr;          // group ops: key → slot table, kept for joins
     u32 dict_log_cap = 0;
     u32 *dense_of_slot = nullptr;
     std::map<std::pair<const vb_shuf *, u32>, JoinPlan> join_plans;
@@ -352,7 +352,7 @@ struct AggInput {
 };
 
 template <int IN, int OPK, int TX>
-static int launch_hash_agg_t(vb_shuf *s, int klass, const u64 *a, const u64 *b, u64 n, Slot *tab, u32 log_cap,
+static int launch_hash_agg_t(vb_shuf *s, int klass, const u64 *a, const u64 *b, u64 n, void *tab, u32 log_cap,
                              TableCtl *ctl, u64 max_inserts, u32 *slot_out)
 {
     vb_ctx *c = s->ctx;
@@ -362,12 +362,12 @@ static int launch_hash_agg_t(vb_shuf *s, int klass, const u64 *a, const u64 *b, 
     u64 grid = std::min<u64>(tiles, (u64)c->sm_count * occ);
     if (grid == 0) return VB_OK;
     KLaunch kl(s, klass, n);
-    kern<<<(unsigned)grid, HA_THREADS, 0, c->stream>>>(a, b, n, tab, log_cap, ctl, max_inserts, slot_out);
+    kern<<<(unsigned)grid, HA_THREADS, 0, c->stream>>>(a, b, n, table_at(tab, log_cap), ctl, max_inserts, slot_out);
     return kl.done("hash_agg_kernel");
 }
 
 template <int IN>
-static int launch_hash_agg_in(vb_shuf *s, int klass, int opk, int tx, const u64 *a, const u64 *b, u64 n, Slot *tab,
+static int launch_hash_agg_in(vb_shuf *s, int klass, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
                               u32 log_cap, TableCtl *ctl, u64 mi, u32 *so)
 {
 #define HA(O, T) return launch_hash_agg_t<IN, O, T>(s, klass, a, b, n, tab, log_cap, ctl, mi, so)
@@ -389,7 +389,7 @@ static int launch_hash_agg_in(vb_shuf *s, int klass, int opk, int tx, const u64 
     return set_err(VB_ERR_UNSUPPORTED, "hash_agg: unsupported op %d for input mode %d", opk, IN);
 }
 
-static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, Slot *tab,
+static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
                            u32 log_cap, TableCtl *ctl, u64 mi, u32 *so)
 {
     switch (in) {
@@ -406,7 +406,7 @@ constexpr u32 MAX_LOG_CAP = 31;
 // Feed every input into one fresh table; on overflow (abort flag) start again 4x larger.
 // slot_out (OPK_DICT): one u32 per row over the concatenation of the inputs.
 static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &inputs, int opk, int tx, u64 hint_distinct,
-                       Slot **out_tab, u32 *out_log_cap, u64 *out_inserted, u32 *slot_out)
+                       void **out_tab, u32 *out_log_cap, u64 *out_inserted, u32 *slot_out)
 {
     vb_ctx *c = s->ctx;
     u64 total = 0;
@@ -432,11 +432,11 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
     for (;;) {
         const u64 cap = 1ull << log_cap;
         DevBuf tab(c);
-        TRY(tab.alloc((cap + 1) * sizeof(Slot)));
+        TRY(tab.alloc(table_bytes(log_cap)));
         {
             KLaunch kl(s, K_MISC);
-            u64 blocks = std::min<u64>((cap + 1 + 255) / 256, (u64)c->sm_count * 8);
-            table_init_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(tab.as<Slot>(), cap, op_identity(opk));
+            u64 blocks = std::min<u64>((cap + BUCKET + 255) / 256, (u64)c->sm_count * 8);
+            table_init_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(table_at(tab.p, log_cap), op_identity(opk));
             TRY(kl.done("table_init_kernel"));
         }
         CU(cudaMemsetAsync(ctl.p, 0, sizeof(TableCtl), c->stream));
@@ -445,7 +445,7 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
         for (auto &in : inputs) {
             if (in.n == 0) continue;
             if (in.loc != VB_HOST) {
-                TRY(launch_hash_agg(s, klass, in.in, opk, tx, in.a, in.b, in.n, tab.as<Slot>(), log_cap, ctl.as<TableCtl>(),
+                TRY(launch_hash_agg(s, klass, in.in, opk, tx, in.a, in.b, in.n, tab.p, log_cap, ctl.as<TableCtl>(),
                                     max_inserts, slot_out ? slot_out + row_base : nullptr));
             } else {
                 const u64 chunk = std::min(in.n, HOST_CHUNK_ROWS);
@@ -464,7 +464,7 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
                             s->st.h2d_bytes += m * 8;
                         }
                     }
-                    TRY(launch_hash_agg(s, klass, in.in, opk, tx, da, db, m, tab.as<Slot>(), log_cap, ctl.as<TableCtl>(),
+                    TRY(launch_hash_agg(s, klass, in.in, opk, tx, da, db, m, tab.p, log_cap, ctl.as<TableCtl>(),
                                         max_inserts, nullptr));
                 }
             }
@@ -473,7 +473,7 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
         CU(cudaMemcpyAsync(h_ctl, ctl.p, sizeof(TableCtl), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (!h_ctl->abort) {
-            *out_tab = (Slot *)tab.release();
+            *out_tab = tab.release();
             *out_log_cap = log_cap;
             *out_inserted = h_ctl->n_inserted;
             s->st.table_slots = std::max<u64>(s->st.table_slots, cap);
@@ -874,7 +874,8 @@ static int seal_group(vb_shuf *s, const Gathered &g)
     DevBuf ckeys(c), cslot(c);
     TRY(ckeys.alloc(max_d * 8));
     TRY(cslot.alloc(max_d * 8));
-    Loader lt{LD_TABLE_KI, s->dict, nullptr, cap};
+    const Table dt = table_at(s->dict, s->dict_log_cap);
+    Loader lt{LD_TABLE_KI, dt.keys, nullptr, cap};
     TRY(multisplit(s, lt, cap + 1, DG_BUCKET, R, max_d, ckeys.as<u64>(), cslot.as<u64>(), s->bucket_off));
     const u64 D = s->bucket_off[R];
     // 3. slot → dense id (bucket-major)
@@ -933,7 +934,7 @@ static int seal_group(vb_shuf *s, const Gathered &g)
 
 // Merge the per-map combined tables of this process into one (ShuffledRdd::compute's
 // merge_combiners loop, shuffled_rdd.rs:154-164, for the partitions held locally).
-static int merge_map_tables(vb_shuf *s, Slot **tab, u32 *log_cap, u64 *n_ins)
+static int merge_map_tables(vb_shuf *s, void **tab, u32 *log_cap, u64 *n_ins)
 {
     std::vector<MapOut *> ts;
     for (auto &m : s->maps) if (m.present && m.table) ts.push_back(&m);
@@ -946,7 +947,8 @@ static int merge_map_tables(vb_shuf *s, Slot **tab, u32 *log_cap, u64 *n_ins)
     std::vector<AggInput> in;
     u64 max_ins = 0;
     for (auto *m : ts) {
-        in.push_back(AggInput{IN_TABLE, (const u64 *)m->table, nullptr, (1ull << m->log_cap) + 1, VB_DEVICE});
+        const Table mt = table_at(m->table, m->log_cap);
+        in.push_back(AggInput{IN_TABLE, mt.keys, mt.accs, (1ull << m->log_cap) + 1, VB_DEVICE});
         max_ins = std::max(max_ins, m->n_inserted);
     }
     TRY(build_table(s, K_MERGE, in, merge_opk(s), TX_NONE, std::max<u64>(max_ins, s->hint), tab, log_cap, n_ins, nullptr));
@@ -955,7 +957,7 @@ static int merge_map_tables(vb_shuf *s, Slot **tab, u32 *log_cap, u64 *n_ins)
 }
 
 // Final (K, C) rows of a combined table, grouped by reduce partition.
-static int finalize_reduce(vb_shuf *s, Slot *tab, u32 log_cap, u64 n_ins)
+static int finalize_reduce(vb_shuf *s, void *tab, u32 log_cap, u64 n_ins)
 {
     vb_ctx *c = s->ctx;
     const u32 R = s->n_reduce;
@@ -967,7 +969,8 @@ static int finalize_reduce(vb_shuf *s, Slot *tab, u32 log_cap, u64 n_ins)
     DevBuf k(c), v(c);
     TRY(k.alloc(max_d * 8));
     TRY(v.alloc(max_d * 8));
-    Loader lt{LD_TABLE_KV, tab, nullptr, cap};
+    const Table ft = table_at(tab, log_cap);
+    Loader lt{LD_TABLE_KV, ft.keys, ft.accs, cap};
     TRY(multisplit(s, lt, cap + 1, DG_BUCKET, R, max_d, k.as<u64>(), v.as<u64>(), s->bucket_off));
     const u64 D = s->bucket_off[R];
     const int tx = val_tx(s);
@@ -1055,7 +1058,7 @@ extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
     CU(cudaSetDevice(c->device));
     std::vector<u64> off;
     if (is_reduce_op(s->agg)) {
-        Slot *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+        void *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
         TRY(merge_map_tables(s, &tab, &log_cap, &n_ins));
         off.assign((size_t)s->world + 1, 0);
         if (tab) {
@@ -1063,7 +1066,8 @@ extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
             DevBuf k(c), v(c);
             TRY(k.alloc((n_ins + 1) * 8));
             TRY(v.alloc((n_ins + 1) * 8));
-            Loader lt{LD_TABLE_KV, tab, nullptr, 1ull << log_cap};
+            const Table et = table_at(tab, log_cap);
+            Loader lt{LD_TABLE_KV, et.keys, et.accs, 1ull << log_cap};
             TRY(multisplit(s, lt, (1ull << log_cap) + 1, DG_DEST, s->world, n_ins + 1, k.as<u64>(), v.as<u64>(), off));
             s->exp_keys = (u64 *)k.release();
             s->exp_vals = (u64 *)v.release();
@@ -1132,7 +1136,7 @@ extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
                 for (u32 m = 0; m < s->n_map; ++m)
                     if (!s->maps[m].present) return set_err(VB_ERR_STATE, "shuffle %llu sealed but map %u was never submitted", (unsigned long long)s->id, m);
                 if (is_reduce_op(s->agg)) {
-                    Slot *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+                    void *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
                     TRY(merge_map_tables(s, &tab, &log_cap, &n_ins));
                     DevBuf guard(c); guard.p = tab;
                     TRY(finalize_reduce(s, tab, log_cap, n_ins));
@@ -1144,7 +1148,7 @@ extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
             } else {
                 if (!s->exported || !s->imported) return set_err(VB_ERR_STATE, "world > 1: seal needs export_prepare + import");
                 if (is_reduce_op(s->agg)) {
-                    Slot *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+                    void *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
                     if (s->imp_n) {
                         std::vector<AggInput> in(1);
                         in[0] = AggInput{IN_SOA, s->imp_keys, s->imp_vals, s->imp_n, VB_DEVICE};
@@ -1292,9 +1296,9 @@ static int join_plan(vb_shuf *l, vb_shuf *r, u32 rid, JoinPlan **out)
         TRY(tot.alloc(8));
         {
             KLaunch kl(l, K_JOIN);
-            join_probe_kernel<<<(p.nl + 255) / 256, 256, 0, c->stream>>>(l->res_keys, l->res_offs, (u32)lb, (u32)le, r->dict,
-                                                                         r->dict_log_cap, r->dense_of_slot, r->res_offs,
-                                                                         cnt.as<u64>(), match.as<u32>());
+            join_probe_kernel<<<(p.nl + 255) / 256, 256, 0, c->stream>>>(l->res_keys, l->res_offs, (u32)lb, (u32)le,
+                                                                         table_at(r->dict, r->dict_log_cap), r->dense_of_slot,
+                                                                         r->res_offs, cnt.as<u64>(), match.as<u32>());
             TRY(kl.done("join_probe_kernel"));
         }
         TRY(exclusive_scan_u64(l, cnt.as<u64>(), pos.as<u64>(), p.nl, tot.as<u64>()));

@@ -15,14 +15,32 @@
 namespace vb {
 
 // ---------------------------------------------------------------------------------------------
-// Hash table
+// Hash table: open addressing over 4-key buckets, keys and accumulators in separate arrays.
+//
+// Measured on B200 (profiles/r1_micro_*.log): a random 8..32-byte read of an L2-resident table
+// sustains ~2.5e11 probes/s and a 64-bit RED ~1.5e11/s, but a *dependent* linear-probing loop
+// (30-46 % of rows need a second probe at load 0.48) serialises L2 latencies inside divergent
+// warps and ran 6x slower.  So a bucket is the 4 keys of one 32-byte sector, fetched with a single
+// 256-bit load (LDG.E.NA.256): at load <= 0.6 almost every row resolves in its first probe and the
+// kernel issues all probes of a tile before consuming any.  L1::no_allocate on the probes keeps
+// the REDs that follow from invalidating L1 lines.
 // ---------------------------------------------------------------------------------------------
-struct __align__(16) Slot {
-    u64 key;
-    u64 acc;
+struct Table {
+    u64 *keys;    // [cap + 4]: keys[cap] is the marker of the special slot (1 = EMPTY_KEY present)
+    u64 *accs;    // [cap + 4]: combiner per slot (reduce ops); unused by the dictionary
+    u32 log_cap;  // cap = 1 << log_cap slots = cap / 4 buckets; log_cap >= 2
 };
 constexpr u64 EMPTY_KEY = ~0ull;
-// tab[cap] is the dedicated home of a real key equal to EMPTY_KEY: .key = 1 when present.
+constexpr u32 BUCKET = 4;
+VB_HD size_t table_bytes(u32 log_cap) { return (((size_t)1 << log_cap) + BUCKET) * 16; }
+VB_HD Table table_at(void *base, u32 log_cap)
+{
+    Table t;
+    t.keys = (u64 *)base;
+    t.accs = (u64 *)base + (((size_t)1 << log_cap) + BUCKET);
+    t.log_cap = log_cap;
+    return t;
+}
 
 struct TableCtl {
     u32 abort;        // set by the kernel: table too full / probe sequence too long → host restarts
@@ -45,52 +63,78 @@ VB_D void op_red(u64 *acc, u64 v)
     else if (OPK == OPK_MAX_U64) atomicMax((unsigned long long *)acc, (unsigned long long)v);
 }
 
-__global__ void table_init_kernel(Slot *tab, u64 cap, u64 identity)
+__global__ void table_init_kernel(Table t, u64 identity)
 {
+    const u64 cap = 1ull << t.log_cap;
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 stride = (u64)gridDim.x * blockDim.x;
-    for (; i <= cap; i += stride) {
-        Slot s;
-        s.key = (i == cap) ? 0ull : EMPTY_KEY;
-        s.acc = identity;
-        tab[i] = s;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < cap + BUCKET; i += stride) {
+        t.keys[i] = (i >= cap) ? 0ull : EMPTY_KEY;
+        t.accs[i] = identity;
     }
+}
+
+struct Bucket4 { u64 k0, k1, k2, k3; };
+
+// one 32-byte sector: 4 candidate keys
+VB_D Bucket4 ld_bucket(const u64 *p)
+{
+    Bucket4 b;
+    asm volatile("ld.global.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(b.k0), "=l"(b.k1), "=l"(b.k2), "=l"(b.k3)
+                 : "l"(p));
+    return b;
+}
+VB_D int bucket_find(const Bucket4 &b, u64 key)
+{
+    return b.k0 == key ? 0 : b.k1 == key ? 1 : b.k2 == key ? 2 : b.k3 == key ? 3 : -1;
 }
 
 constexpr int HA_THREADS = 256;
 constexpr int HA_ROWS = 4;
 constexpr int HA_TILE = HA_THREADS * HA_ROWS;
-constexpr u32 HA_MAX_PROBE = 512;
+constexpr u32 HA_MAX_PROBE = 256;   // buckets
 
-// Probe/insert `key`; on success returns the slot index.  `inserted` counts new keys.
+VB_D u64 home_bucket(u64 key, u32 log_cap) { return slot_hash(key) >> (64 - (log_cap - 2)); }
+
+// Resolve `key` starting from bucket `b` whose content `bk` is already loaded: find it, or claim the
+// first empty slot with a CAS, or move on to the next bucket.  Slots only ever go EMPTY → key and are
+// claimed first-empty-first, so a key can never end up in two slots (a stale view is an older view).
 template <int OPK>
-VB_D bool table_upsert(Slot *tab, u64 mask, u32 shift, u64 key, u64 v, u32 &slot_idx, u32 &inserted)
+VB_D bool table_resolve(const Table &t, u64 b, Bucket4 bk, u64 key, u64 v, u32 &slot_idx, u32 &inserted)
 {
-    u64 s = slot_hash(key) >> shift;
+    const u64 nb_mask = (1ull << (t.log_cap - 2)) - 1;
 #pragma unroll 1
     for (u32 probe = 0; probe < HA_MAX_PROBE; ++probe) {
-        u64 k = ld_cg_u64(&tab[s].key);
-        if (k == EMPTY_KEY) {
-            k = atomicCAS((unsigned long long *)&tab[s].key, (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-            if (k == EMPTY_KEY) { ++inserted; k = key; }
+        int hit = bucket_find(bk, key);
+        if (hit < 0) {
+            const int e = bucket_find(bk, EMPTY_KEY);
+            if (e < 0) {
+                b = (b + 1) & nb_mask;
+            } else {
+                const u64 old = atomicCAS((unsigned long long *)&t.keys[4 * b + e], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (old == EMPTY_KEY) { ++inserted; hit = e; }
+                else if (old == key) hit = e;
+            }
         }
-        if (k == key) {
-            op_red<OPK>(&tab[s].acc, v);
+        if (hit >= 0) {
+            const u64 s = 4 * b + (u64)hit;
+            op_red<OPK>(&t.accs[s], v);
             slot_idx = (u32)s;
             return true;
         }
-        s = (s + 1) & mask;
+        bk = ld_bucket(&t.keys[4 * b]);
     }
     return false;
 }
 
 // One pass over n rows.  IN_AOS: a = rows (16 B each).  IN_SOA: a = keys, b = vals (b may be
-// NULL for COUNT/DICT).  IN_TABLE: a = source Slot table of n-1 slots + the special slot.
+// NULL for COUNT/DICT).  IN_TABLE: a/b = keys/accs of a source table of n-1 slots + the special slot.
 // TX: order-preserving value transform applied on load (MIN/MAX over i64/f64).
 template <int IN, int OPK, int TX>
 __global__ void __launch_bounds__(HA_THREADS)
-hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Slot *tab, u32 log_cap, TableCtl *ctl,
-                u64 max_inserts, u32 *__restrict__ slot_out)
+hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Table t, TableCtl *ctl, u64 max_inserts,
+                u32 *__restrict__ slot_out)
 {
     __shared__ u32 s_inserts;
     __shared__ u32 s_abort;
@@ -98,9 +142,7 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Slo
     if (tid == 0) { s_inserts = 0; s_abort = 0; }
     __syncthreads();
     const u64 pol = policy_evict_first();
-    const u64 cap = 1ull << log_cap;
-    const u64 mask = cap - 1;
-    const u32 shift = 64 - log_cap;
+    const u64 cap = 1ull << t.log_cap;
     const u64 n_tiles = (n + HA_TILE - 1) / HA_TILE;
     u32 my_inserts = 0;
     u32 iter = 0;
@@ -121,12 +163,20 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Slo
                     k[j] = ld_stream_u64(a + idx, pol);
                     if (OPK != OPK_COUNT && OPK != OPK_DICT) v[j] = ld_stream_u64(b + idx, pol);
                 } else {
-                    ulonglong2 r = ld_stream_u64x2(a + 2 * idx, pol);
-                    k[j] = r.x; v[j] = r.y;
-                    if (idx == n - 1) { ok[j] = (r.x == 1ull); k[j] = EMPTY_KEY; }   // special slot
-                    else if (r.x == EMPTY_KEY) ok[j] = false;                        // unoccupied
+                    k[j] = ld_stream_u64(a + idx, pol);
+                    v[j] = ld_stream_u64(b + idx, pol);
+                    if (idx == n - 1) { ok[j] = (k[j] == 1ull); k[j] = EMPTY_KEY; }   // special slot
+                    else if (k[j] == EMPTY_KEY) ok[j] = false;                       // unoccupied
                 }
             }
+        }
+        // all first probes of the tile in flight before any is consumed
+        u64 hb[HA_ROWS];
+        Bucket4 bk[HA_ROWS];
+#pragma unroll
+        for (int j = 0; j < HA_ROWS; ++j) {
+            hb[j] = home_bucket(k[j], t.log_cap);
+            if (ok[j] && k[j] != EMPTY_KEY) bk[j] = ld_bucket(&t.keys[4 * hb[j]]);
         }
 #pragma unroll
         for (int j = 0; j < HA_ROWS; ++j) {
@@ -135,10 +185,10 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Slo
             const u64 val = (TX == TX_NONE) ? v[j] : tx_fwd(v[j], TX);
             u32 slot = 0;
             if (k[j] == EMPTY_KEY) {
-                tab[cap].key = 1ull;
-                op_red<OPK>(&tab[cap].acc, val);
+                t.keys[cap] = 1ull;
+                op_red<OPK>(&t.accs[cap], val);
                 slot = (u32)cap;
-            } else if (!table_upsert<OPK>(tab, mask, shift, k[j], val, slot, my_inserts)) {
+            } else if (!table_resolve<OPK>(t, hb[j], bk[j], k[j], val, slot, my_inserts)) {
                 atomicExch(&ctl->abort, 1u);
             }
             if (OPK == OPK_DICT) st_stream_u32(slot_out + idx, slot);
@@ -167,16 +217,17 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Slo
 }
 
 // Read-only lookup used by the join: slot index of `key`, or 0xFFFFFFFF.
-VB_D u32 table_find(const Slot *tab, u32 log_cap, u64 key)
+VB_D u32 table_find(const Table &t, u64 key)
 {
-    const u64 cap = 1ull << log_cap, mask = cap - 1;
-    if (key == EMPTY_KEY) return tab[cap].key == 1ull ? (u32)cap : 0xFFFFFFFFu;
-    u64 s = slot_hash(key) >> (64 - log_cap);
+    const u64 cap = 1ull << t.log_cap, nb_mask = (cap >> 2) - 1;
+    if (key == EMPTY_KEY) return t.keys[cap] == 1ull ? (u32)cap : 0xFFFFFFFFu;
+    u64 b = home_bucket(key, t.log_cap);
     for (u32 probe = 0; probe <= HA_MAX_PROBE; ++probe) {
-        u64 k = tab[s].key;
-        if (k == key) return (u32)s;
-        if (k == EMPTY_KEY) return 0xFFFFFFFFu;
-        s = (s + 1) & mask;
+        const Bucket4 bk = ld_bucket(&t.keys[4 * b]);
+        const int hit = bucket_find(bk, key);
+        if (hit >= 0) return (u32)(4 * b + hit);
+        if (bucket_find(bk, EMPTY_KEY) >= 0) return 0xFFFFFFFFu;
+        b = (b + 1) & nb_mask;
     }
     return 0xFFFFFFFFu;
 }
@@ -195,8 +246,8 @@ enum : int { LD_SOA64 = 0, LD_AOS64 = 1, LD_KEY32_VAL_SOA = 2, LD_KEY32_VAL_AOS 
 // Where a pass reads its rows from.  One struct, run-time mode (CTA-uniform branch).
 struct Loader {
     int mode;
-    const void *keys;   // u64* / u32* / rows (AoS) / Slot*
-    const void *vals;   // u64* or AoS rows for LD_KEY32_VAL_AOS
+    const void *keys;   // u64* / u32* / rows (AoS) / table keys
+    const void *vals;   // u64* (table modes: the accs array) or AoS rows for LD_KEY32_VAL_AOS
     u64 cap;            // table modes: number of regular slots (row `cap` is the special slot)
 };
 
@@ -223,12 +274,11 @@ VB_D bool rp_load(const Loader &ld, u64 i, KeyT &key, u64 &val, u64 pol)
         return true;
     case LD_TABLE_KV:
     case LD_TABLE_KI: {
-        const Slot *t = (const Slot *)ld.keys;
-        ulonglong2 r = ld_stream_u64x2(&t[i], pol);
-        val = (ld.mode == LD_TABLE_KI) ? i : r.y;
-        if (i == ld.cap) { key = (KeyT)EMPTY_KEY; return r.x == 1ull; }
-        key = (KeyT)r.x;
-        return r.x != EMPTY_KEY;
+        const u64 k = ld_stream_u64((const u64 *)ld.keys + i, pol);
+        val = (ld.mode == LD_TABLE_KI) ? i : ld_stream_u64((const u64 *)ld.vals + i, pol);
+        if (i == ld.cap) { key = (KeyT)EMPTY_KEY; return k == 1ull; }
+        key = (KeyT)k;
+        return k != EMPTY_KEY;
     }
     }
     return false;
@@ -567,13 +617,13 @@ __global__ void aos_to_soa_kernel(const u64 *__restrict__ rows, u64 n, u64 *__re
 // ---------------------------------------------------------------------------------------------
 // For left keys [lb, le): find the key in the right shuffle's dictionary; cnt = lenL * lenR.
 __global__ void join_probe_kernel(const u64 *__restrict__ lkeys, const u64 *__restrict__ loffs, u32 lb, u32 le,
-                                  const Slot *__restrict__ rtab, u32 r_log_cap, const u32 *__restrict__ r_dense,
+                                  Table rtab, const u32 *__restrict__ r_dense,
                                   const u64 *__restrict__ roffs, u64 *__restrict__ cnt, u32 *__restrict__ match)
 {
     u32 j = lb + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= le) return;
     u64 key = lkeys[j];
-    u32 s = table_find(rtab, r_log_cap, key);
+    u32 s = table_find(rtab, key);
     u64 c = 0;
     u32 m = 0xFFFFFFFFu;
     if (s != 0xFFFFFFFFu) {
