@@ -57,6 +57,15 @@ def test_vb_slice_matches_reference_slicing(n, m):
     assert vb.slice_starts(n, m).tolist() == O.slice_starts(n, m).tolist()
 
 
+def test_vb_slice_closed_form_random():
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(0, 3000))
+        m = int(rng.integers(1, 400))
+        assert vb.slice_starts(n, m).tolist() == O.slice_starts(n, m).tolist(), (n, m)
+    assert vb.slice_starts(10 ** 9, 8).tolist() == [i * 125_000_000 for i in range(9)]
+
+
 def test_vb_slice_rejects_zero_slices():
     with pytest.raises(ValueError):
         vb.slice_starts(10, 0)

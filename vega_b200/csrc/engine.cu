@@ -494,12 +494,42 @@ struct PassPlan {
     size_t hist_bytes() const { return ((size_t)RP_NB * num_parts + 1) * sizeof(u32); }
 };
 
+// (LDM, DGM) combinations the engine uses; anything else is a programming error.
+#define RP_COMBOS(X)                                                         \
+    X(LD_SOA64, DG_BITS) X(LD_AOS64, DG_BITS) X(LD_KEY32_VAL_SOA, DG_BITS) X(LD_KEY32_VAL_AOS, DG_BITS) \
+    X(LD_SOA64, DG_BUCKET) X(LD_TABLE_KV, DG_BUCKET) X(LD_TABLE_KI, DG_BUCKET)                           \
+    X(LD_SOA64, DG_DEST) X(LD_AOS64, DG_DEST) X(LD_TABLE_KV, DG_DEST)
+
+template <typename KeyT, int LDM> constexpr bool rp_key_ok()
+{
+    return (LDM == LD_KEY32_VAL_SOA || LDM == LD_KEY32_VAL_AOS) ? sizeof(KeyT) == 4 : sizeof(KeyT) == 8;
+}
+
+template <typename KeyT, bool HAS_VAL>
+static const void *scatter_fn(int ldm, int dgm)
+{
+#define X(L, D) if (ldm == L && dgm == D) { if constexpr (rp_key_ok<KeyT, L>()) return (const void *)rp_scatter_kernel<KeyT, HAS_VAL, L, D>; }
+    RP_COMBOS(X)
+#undef X
+    return nullptr;
+}
+
+template <typename KeyT>
+static const void *hist_fn(int ldm, int dgm)
+{
+#define X(L, D) if (ldm == L && dgm == D) { if constexpr (rp_key_ok<KeyT, L>()) return (const void *)rp_hist_kernel<KeyT, L, D>; }
+    RP_COMBOS(X)
+#undef X
+    return nullptr;
+}
+
 template <typename KeyT, bool HAS_VAL>
 static PassPlan plan_pass(vb_ctx *c, u64 n)
 {
     PassPlan p;
     if (n == 0) return p;
-    auto kern = rp_scatter_kernel<KeyT, HAS_VAL>;
+    // occupancy is the same for every (LDM, DGM) instantiation to within a CTA; use a representative one
+    const void *kern = sizeof(KeyT) == 4 ? scatter_fn<KeyT, HAS_VAL>(LD_KEY32_VAL_SOA, DG_BITS) : scatter_fn<KeyT, HAS_VAL>(LD_SOA64, DG_BITS);
     size_t smem = rp_scatter_smem<KeyT, HAS_VAL>();
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = occupancy(c, kern, RP_THREADS, smem);
@@ -520,9 +550,22 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
 {
     vb_ctx *c = s->ctx;
     if (n == 0 || plan.num_parts == 0) return VB_OK;
+    const void *hk = hist_fn<KeyT>(ld.mode, dg.mode);
+    const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode);
+    if (!hk || !sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d not instantiated", ld.mode, dg.mode);
+    const size_t smem = rp_scatter_smem<KeyT, HAS_VAL>();
+    CU(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const u64 tiles_per_part = plan.rows_per_part / RP_TILE;
+    u32 split = (u32)std::max<u64>(1, std::min<u64>(tiles_per_part, ((u64)c->sm_count * 8 + plan.num_parts - 1) / plan.num_parts));
+    CU(cudaMemsetAsync(d_hist, 0, plan.hist_bytes(), c->stream));
+    u64 rows_per_part = plan.rows_per_part;
+    u32 num_parts = plan.num_parts;
+    Loader ldc = ld;
+    Digit dgc = dg;
     {
         KLaunch kl(s, K_RP_HIST, n);
-        rp_hist_kernel<KeyT><<<plan.num_parts, RP_THREADS, 0, c->stream>>>(ld, dg, n, plan.rows_per_part, d_hist, plan.num_parts);
+        void *args[] = {&ldc, &dgc, &n, &rows_per_part, &d_hist, &num_parts, &split};
+        CU(cudaLaunchKernel(hk, dim3(plan.num_parts * split), dim3(RP_THREADS), args, 0, c->stream));
         TRY(kl.done("rp_hist_kernel"));
     }
     {
@@ -532,8 +575,9 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     }
     {
         KLaunch kl(s, K_RP_SCATTER, n);
-        rp_scatter_kernel<KeyT, HAS_VAL><<<plan.num_parts, RP_THREADS, rp_scatter_smem<KeyT, HAS_VAL>(), c->stream>>>(
-            ld, dg, n, plan.rows_per_part, d_hist, plan.num_parts, out_keys, out_vals);
+        const u32 *ch = d_hist;
+        void *args[] = {&ldc, &dgc, &n, &rows_per_part, &ch, &num_parts, &out_keys, &out_vals};
+        CU(cudaLaunchKernel(sk, dim3(plan.num_parts), dim3(RP_THREADS), args, smem, c->stream));
         TRY(kl.done("rp_scatter_kernel"));
     }
     return VB_OK;
@@ -1426,26 +1470,24 @@ extern "C" uint32_t vb_get_partition(uint64_t key, uint32_t key_width, uint32_t 
     return (uint32_t)(hash_key(key, key_width) % (uint64_t)n_reduce);
 }
 
-// ParallelCollection::slice (src/rdd/parallel_collection_rdd.rs:116-145): contiguous slices with
-// boundaries floor((s+1)*n/num_slices); one cut per element at most, so n < num_slices yields an
-// empty leading slice and n singletons.
+// ParallelCollection::slice (src/rdd/parallel_collection_rdd.rs:116-145).  The reference walks the
+// elements and cuts at most once per element; in closed form that is
+//   n >= num_slices : exactly num_slices slices, slice s = [floor(s*n/num_slices), floor((s+1)*n/num_slices))
+//   n <  num_slices : every element triggers a cut (the running `end` never gets ahead of the element
+//                     index), giving an empty leading slice followed by n singletons (n+1 slices)
+// (tests/test_abi_cpu.py checks this against the literal loop of the oracle).
 extern "C" uint64_t vb_slice(uint64_t n, uint64_t num_slices, uint64_t *starts)
 {
     if (num_slices < 1 || !starts) return 0;
-    uint64_t cut = 0, taken = 0, n_out = 0, first = 0;
-    uint64_t end = ((cut + 1) * n) / num_slices;
-    for (uint64_t i = 0; i < n; ++i) {
-        if (taken >= end) {
-            ++cut;
-            end = ((cut + 1) * n) / num_slices;
-            starts[n_out++] = first;
-            first = i;
-        }
-        ++taken;
+    if (n >= num_slices) {
+        for (uint64_t s = 0; s < num_slices; ++s) starts[s] = (uint64_t)(((unsigned __int128)s * n) / num_slices);
+        starts[num_slices] = n;
+        return num_slices;
     }
-    starts[n_out++] = first;
-    starts[n_out] = n;
-    return n_out;
+    starts[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) starts[i + 1] = i;
+    starts[n + 1] = n;
+    return n + 1;
 }
 
 // ---------------------------------------------------------------------------------------------

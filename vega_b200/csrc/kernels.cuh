@@ -251,40 +251,52 @@ struct Loader {
     u64 cap;            // table modes: number of regular slots (row `cap` is the special slot)
 };
 
-template <typename KeyT>
+// Loader / digit modes are compile-time (LDM, DGM): a run-time switch per item left ptxas with a
+// branch per load and no memory-level parallelism (profiles/r1_ncu_rp_before.txt).
+template <typename KeyT, int LDM>
 VB_D bool rp_load(const Loader &ld, u64 i, KeyT &key, u64 &val, u64 pol)
 {
-    switch (ld.mode) {
-    case LD_SOA64:
+    if constexpr (LDM == LD_SOA64) {
         key = (KeyT)ld_stream_u64((const u64 *)ld.keys + i, pol);
         val = ld.vals ? ld_stream_u64((const u64 *)ld.vals + i, pol) : 0ull;
         return true;
-    case LD_AOS64: {
+    } else if constexpr (LDM == LD_AOS64) {
         ulonglong2 r = ld_stream_u64x2((const u64 *)ld.keys + 2 * i, pol);
         key = (KeyT)r.x; val = r.y;
         return true;
-    }
-    case LD_KEY32_VAL_SOA:
+    } else if constexpr (LDM == LD_KEY32_VAL_SOA) {
         key = (KeyT)ld_stream_u32((const u32 *)ld.keys + i, pol);
         val = ld.vals ? ld_stream_u64((const u64 *)ld.vals + i, pol) : 0ull;
         return true;
-    case LD_KEY32_VAL_AOS:
+    } else if constexpr (LDM == LD_KEY32_VAL_AOS) {
         key = (KeyT)ld_stream_u32((const u32 *)ld.keys + i, pol);
         val = ld_stream_u64((const u64 *)ld.vals + 2 * i + 1, pol);
         return true;
-    case LD_TABLE_KV:
-    case LD_TABLE_KI: {
+    } else {
         const u64 k = ld_stream_u64((const u64 *)ld.keys + i, pol);
-        val = (ld.mode == LD_TABLE_KI) ? i : ld_stream_u64((const u64 *)ld.vals + i, pol);
+        val = (LDM == LD_TABLE_KI) ? i : ld_stream_u64((const u64 *)ld.vals + i, pol);
         if (i == ld.cap) { key = (KeyT)EMPTY_KEY; return k == 1ull; }
         key = (KeyT)k;
         return k != EMPTY_KEY;
     }
-    }
-    return false;
 }
 
-enum : int { DG_BITS = 0, DG_BUCKET = 1, DG_DEST = 2, DG_RANGE = 3 };
+// key only (histogram pass)
+template <typename KeyT, int LDM>
+VB_D bool rp_load_key(const Loader &ld, u64 i, KeyT &key, u64 pol)
+{
+    if constexpr (LDM == LD_SOA64) { key = (KeyT)ld_stream_u64((const u64 *)ld.keys + i, pol); return true; }
+    else if constexpr (LDM == LD_AOS64) { key = (KeyT)ld_stream_u64((const u64 *)ld.keys + 2 * i, pol); return true; }
+    else if constexpr (LDM == LD_KEY32_VAL_SOA || LDM == LD_KEY32_VAL_AOS) { key = (KeyT)ld_stream_u32((const u32 *)ld.keys + i, pol); return true; }
+    else {
+        const u64 k = ld_stream_u64((const u64 *)ld.keys + i, pol);
+        if (i == ld.cap) { key = (KeyT)EMPTY_KEY; return k == 1ull; }
+        key = (KeyT)k;
+        return k != EMPTY_KEY;
+    }
+}
+
+enum : int { DG_BITS = 0, DG_BUCKET = 1, DG_DEST = 2 };
 
 // Which bin a key goes to.  DG_BITS: radix digit of the (order-transformed) key.  DG_BUCKET:
 // digit of HashPartitioner::get_partition(key).  DG_DEST: owning rank = partition % world.
@@ -297,43 +309,71 @@ struct Digit {
     FastMod fm_world;  // % world
 };
 
-template <typename KeyT>
+template <typename KeyT, int DGM>
 VB_D u32 rp_digit(const Digit &dg, KeyT key)
 {
-    if (dg.mode == DG_BITS) {
+    if constexpr (DGM == DG_BITS) {
         u64 k = (sizeof(KeyT) == 8) ? tx_fwd((u64)key, dg.tx) : (u64)key;
         return (u32)(k >> dg.shift) & dg.mask;
+    } else {
+        u32 b = get_partition((u64)key, dg.key_width, dg.fm);
+        if constexpr (DGM == DG_DEST) return fastmod(b, dg.fm_world);
+        return (b >> dg.shift) & dg.mask;
     }
-    u32 b = get_partition((u64)key, dg.key_width, dg.fm);
-    if (dg.mode == DG_DEST) return fastmod(b, dg.fm_world);
-    return (b >> dg.shift) & dg.mask;
 }
 
-// part p covers rows [p*rows_per_part, min(n, (p+1)*rows_per_part)); hist[d*num_parts + p]
-template <typename KeyT>
+// Lanes of the warp whose 9-bit digit equals mine.  Built from 9 ballots (one per bit) instead of
+// MATCH.ANY: the hardware match iterates over the distinct values in the warp (~30 for random
+// digits) and dominated both radix kernels (profiles/r1_ncu_rp_match_any.txt: short_scoreboard).
+VB_D u32 warp_match_digit(u32 d)
+{
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const u32 m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+// part p covers rows [p*rows_per_part, min(n, (p+1)*rows_per_part)); hist[d*num_parts + p].
+// Each part is histogrammed by `split` CTAs (blockIdx.x = part*split + sub) that add their counts
+// with global atomics, so the grid fills the machine even though there are only ~2 parts per SM.
+// hist must be zeroed before the launch.
+template <typename KeyT, int LDM, int DGM>
 __global__ void __launch_bounds__(RP_THREADS)
-rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ hist, u32 num_parts)
+rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ hist, u32 num_parts, u32 split)
 {
     __shared__ u32 cnt[RP_WARPS][RP_NB + 1];
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     for (u32 d = tid; d < RP_WARPS * (RP_NB + 1); d += RP_THREADS) (&cnt[0][0])[d] = 0;
     __syncthreads();
     const u64 pol = policy_evict_first();
-    const u32 part = blockIdx.x;
+    const u32 part = blockIdx.x / split, sub = blockIdx.x % split;
     const u64 begin = (u64)part * rows_per_part;
     const u64 end = min(n, begin + rows_per_part);
-    for (u64 t0 = begin; t0 < end; t0 += RP_TILE) {
-#pragma unroll 4
-        for (int i = 0; i < RP_ITEMS; ++i) {
-            const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)i * 32 + lane;
-            u32 d = RP_NB;
-            if (idx < end) {
-                KeyT key; u64 val;
-                if (rp_load<KeyT>(ld, idx, key, val, pol)) d = rp_digit<KeyT>(dg, key);
+    constexpr int HB = 8;   // items per batch: keeps the u64 instantiation at <= 64 registers
+    for (u64 t0 = begin + (u64)sub * RP_TILE; t0 < end; t0 += (u64)split * RP_TILE) {
+#pragma unroll 1
+        for (int h = 0; h < RP_ITEMS; h += HB) {
+            u32 dig[HB];
+            KeyT key[HB];
+            bool ok[HB];
+#pragma unroll
+            for (int i = 0; i < HB; ++i) {
+                const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)(h + i) * 32 + lane;
+                key[i] = 0;
+                ok[i] = (idx < end) && rp_load_key<KeyT, LDM>(ld, idx, key[i], pol);
             }
-            const u32 peers = __match_any_sync(0xffffffffu, d);
-            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] += __popc(peers);
-            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < HB; ++i) dig[i] = ok[i] ? rp_digit<KeyT, DGM>(dg, key[i]) : (u32)RP_NB;
+#pragma unroll
+            for (int i = 0; i < HB; ++i) {
+                const u32 peers = warp_match_digit(dig[i]);
+                if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][dig[i]] += __popc(peers);
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
@@ -341,7 +381,7 @@ rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ 
         u32 s = 0;
 #pragma unroll
         for (int w = 0; w < RP_WARPS; ++w) s += cnt[w][d];
-        hist[(u64)d * num_parts + part] = s;
+        if (s) atomicAdd(&hist[(u64)d * num_parts + part], s);
     }
 }
 
@@ -384,7 +424,7 @@ __global__ void __launch_bounds__(1024) rp_scan_kernel(u32 *hist, u32 len)
     if (tid == 0) hist[len] = s_total;
 }
 
-template <typename KeyT, bool HAS_VAL>
+template <typename KeyT, bool HAS_VAL, int LDM, int DGM>
 __global__ void __launch_bounds__(RP_THREADS)
 rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
                   KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals)
@@ -414,20 +454,19 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
         KeyT key[RP_ITEMS];
         u64 val[RP_ITEMS];
         unsigned short dig[RP_ITEMS], rank[RP_ITEMS];
+        bool ok[RP_ITEMS];
 #pragma unroll
-        for (int i = 0; i < RP_ITEMS; ++i) {
+        for (int i = 0; i < RP_ITEMS; ++i) {   // every load of the tile is issued before any is used
             const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)i * 32 + lane;
-            u32 d = RP_NB;
             key[i] = 0; val[i] = 0;
-            if (idx < end) {
-                if (rp_load<KeyT>(ld, idx, key[i], val[i], pol)) d = rp_digit<KeyT>(dg, key[i]);
-            }
-            dig[i] = (unsigned short)d;
+            ok[i] = (idx < end) && rp_load<KeyT, LDM>(ld, idx, key[i], val[i], pol);
         }
+#pragma unroll
+        for (int i = 0; i < RP_ITEMS; ++i) dig[i] = (unsigned short)(ok[i] ? rp_digit<KeyT, DGM>(dg, key[i]) : (u32)RP_NB);
 #pragma unroll
         for (int i = 0; i < RP_ITEMS; ++i) {
             const u32 d = dig[i];
-            const u32 peers = __match_any_sync(0xffffffffu, d);
+            const u32 peers = warp_match_digit(d);
             const u32 base = cnt[warp][d];
             __syncwarp();
             if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = base + __popc(peers);

@@ -97,18 +97,24 @@ def all_to_all_v(send_keys, send_vals, send_counts, group=None):
 
 
 def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, world, group=None, key_width=8, hint=0,
-                stats=None):
+                stats=None, exchange_device=None):
     """Map side on this rank's partitions → exchange → reduce side for the partitions this rank owns.
 
     local_maps: [(map_id, keys, vals_or_None)], ascending map ids from map_block(rank, world, n_map).
     Returns the sealed engine handle; engine.reduce(h, r) is non-empty only for r % world == rank.
+    exchange_device: move the packed buffers there for the collective (tests: "cpu" + gloo on a 1-GPU box).
     """
     sh = engine.create(n_map, n_reduce, kcode, vcode, agg, rank, world, key_width=key_width, hint=hint)
     for map_id, keys, vals in local_maps:
         engine.map(sh, map_id, keys, vals)
     if world > 1:
         counts, sk, sv = engine.export(sh, world)
+        home = sk.device
+        if exchange_device is not None:        # e.g. "cpu" for a gloo group: stage the exchange through the host
+            sk, sv = sk.to(exchange_device), sv.to(exchange_device)
         rk, rv, rcounts = all_to_all_v(sk, sv, counts, group)
+        if exchange_device is not None:
+            rk, rv = rk.to(home), rv.to(home)
         if stats is not None:
             stats["sent_rows"] = sum(counts) - counts[rank]
             stats["recv_rows"] = sum(rcounts) - rcounts[rank]
