@@ -181,7 +181,7 @@ def main():
 
     def step(stats=None):
         sh = vdist.run_shuffle(engine, maps, n_map_global, n_red_global, L.VB_U64, L.VB_U64, L.VB_AGG_SUM, rank, world,
-                               group=pg, hint=D, stats=stats)
+                               group=pg, stats=stats)
         return sh
 
     for _ in range(args.warmup):
@@ -251,7 +251,9 @@ def main():
             "clocks": clocks,
             "gpu_launches": agg["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "hash_agg_kernel<IN_AOS,OPK_ADD_U64>",
+                         "traffic": (2.03898e9 if abs(rows_per_launch - 1.25e8) < 1 else None),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r1_ncu_hash_agg_bucketized.txt (1.25e8-row launch)",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "hash_agg_kernel<IN_AOS,OPK_ADD_U64>",
                          "rows_per_launch": rows_per_launch, "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
                          "step_share": agg["hot_ms"] / max(ms_total, 1e-9),
                          "whole_step_frac": (N * ALG_BYTES_PER_PAIR + 16.0 * D) / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -259,7 +261,12 @@ def main():
             "parity": {"distinct_keys_out": chk_keys, "sum_matches_input": True if world == 1 else None},
         }
         if world > 1:
-            out["exchange"] = {"rows_sent_per_rank_per_step": xstats.get("sent_rows"), "bytes_per_row": 16}
+            sent = xstats.get("sent_rows") or 0
+            xms = (xstats.get("exchange_ms") or 0.0) / max(xstats.get("exchanges", 1), 1)
+            out["exchange"] = {"collective": "one all-to-all-v per column (NCCL) of the map-side-combined rows",
+                               "rows_sent_per_rank_per_step": sent, "bytes_sent_per_rank_per_step": 16 * sent,
+                               "ms_per_step": xms, "GBps_per_rank": (16 * sent / (xms * 1e-3) / 1e9) if xms > 0 else None,
+                               "note": "latency-bound: map-side combine shrinks 16 GB/rank of rows to <= 16 MB"}
 
     # ---------------------------------------------------------------- e2e (public API, host buffers)
     if not args.no_e2e:
@@ -277,12 +284,12 @@ def main():
 
         def e2e_step():
             if world == 1:
-                k, c = sc.parallelize(hostnp, M).reduce_by_key("sum", R, hint=D).collect()
+                k, c = sc.parallelize(hostnp, M).reduce_by_key("sum", R).collect()
                 return len(k), 0, 16 * len(k)
             st = vb.slice_starts(n_e2e, M)
             mp = [(lo + m, hostnp[int(st[m]):int(st[m + 1])], None) for m in range(len(st) - 1)]
             sh = vdist.run_shuffle(engine, mp, n_map_global, n_red_global, L.VB_U64, L.VB_U64, L.VB_AGG_SUM, rank, world,
-                                   group=pg, hint=D)
+                                   group=pg)
             nk = 0
             for r in vdist.owned_partitions(rank, world, n_red_global):
                 k, c = sh.reduce(r)
@@ -317,7 +324,7 @@ def main():
         threads = min(M, nproc)
         times = cpu_port_run(n_cpu, D, M, R, threads, 2, 1)
         out["cpu_baseline"] = {"value": n_cpu * len(times) / sum(times), "unit": "pairs/s", "cores": threads, "kind": "port",
-                               "host_cores": nproc,
+                               "host_cores": nproc, "cores_note": "vega runs one task per partition: 8 map then 8 reduce tasks, so 8 threads is all this config can use",
                                "sample": f"first {n_cpu:.0e} pairs of the same generator, {M}x{R} partitions, 2 timed runs; C restatement of vega's algorithm (oracle/vega_oracle.c), not vega itself (Rust, unbuildable here)"}
     if rank == 0:
         print(json.dumps(out))

@@ -226,6 +226,7 @@ struct vb_shuf {
     int kdt = 0, vdt = 0, agg = 0, part = 0;
     u32 key_width = 8;
     u64 hint = 0;
+    u64 learned_distinct = 0;      // distinct keys seen by the previous table build of this shuffle
     u32 rank = 0, world = 1;
     std::vector<MapOut> maps;
     std::mutex mu;
@@ -403,6 +404,63 @@ static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const
 constexpr u64 HOST_CHUNK_ROWS = 32ull << 20;   // host inputs are streamed through a 512 MiB stage
 constexpr u32 MAX_LOG_CAP = 31;
 
+static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
+                           u32 log_cap, TableCtl *ctl, u64 mi, u32 *so);
+
+// Distinct-count estimate from a strided sample of up to 2^20 keys of the first device-resident
+// input: insert the sample into a scratch dictionary, read the number of distinct keys d_s, and
+// solve d_s = D (1 - exp(-s / D)) for D (keys assumed roughly equally frequent).  Returns 0 when
+// there is nothing to sample; a sample that is ~all distinct only proves D >~ 25 s.
+static int estimate_distinct(vb_shuf *s, const std::vector<AggInput> &inputs, u64 total, u64 *out)
+{
+    vb_ctx *c = s->ctx;
+    *out = 0;
+    const AggInput *src = nullptr;
+    for (auto &in : inputs)
+        if (in.loc != VB_HOST && in.n && (in.in == IN_AOS || in.in == IN_SOA)) { src = &in; break; }
+    if (!src) return VB_OK;
+    const u32 m = (u32)std::min<u64>(src->n, 1u << 20);
+    const u64 stride = std::max<u64>(1, src->n / m);
+    const u32 log_cap = 21;
+    DevBuf keys(c), tab(c), ctl(c), slots(c);
+    TRY(keys.alloc((size_t)m * 8));
+    TRY(slots.alloc((size_t)m * 4));
+    TRY(tab.alloc(table_bytes(log_cap)));
+    TRY(ctl.alloc(sizeof(TableCtl)));
+    CU(cudaMemsetAsync(ctl.p, 0, sizeof(TableCtl), c->stream));
+    {
+        KLaunch kl(s, K_MISC);
+        table_init_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(table_at(tab.p, log_cap), 0);
+        TRY(kl.done("table_init_kernel"));
+    }
+    {
+        KLaunch kl(s, K_MISC);
+        if (src->in == IN_AOS) sample_keys_kernel<IN_AOS><<<(m + 255) / 256, 256, 0, c->stream>>>(src->a, src->n, stride, keys.as<u64>(), m);
+        else sample_keys_kernel<IN_SOA><<<(m + 255) / 256, 256, 0, c->stream>>>(src->a, src->n, stride, keys.as<u64>(), m);
+        TRY(kl.done("sample_keys_kernel"));
+    }
+    TRY(launch_hash_agg(s, K_MISC, IN_SOA, OPK_DICT, TX_NONE, keys.as<u64>(), nullptr, m, tab.p, log_cap, ctl.as<TableCtl>(), ~0ull,
+                        slots.as<u32>()));
+    TableCtl *h = (TableCtl *)c->h_scratch;
+    CU(cudaMemcpyAsync(h, ctl.p, sizeof(TableCtl), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double ds = (double)h->n_inserted + 1.0, sm = (double)m;
+    double D;
+    if (ds >= 0.98 * sm) {
+        D = std::min<double>((double)total, 32.0 * sm);     // unresolved: at least ~25 s distinct keys
+        if (src->n <= m) D = ds;                             // the sample was the whole input
+    } else {
+        double lo = ds, hi = 64.0 * sm;                      // d(D) = D (1 - exp(-s/D)) is increasing in D
+        for (int it = 0; it < 60; ++it) {
+            double mid = 0.5 * (lo + hi);
+            if (mid * (1.0 - exp(-sm / mid)) < ds) lo = mid; else hi = mid;
+        }
+        D = hi;
+    }
+    *out = (u64)std::min<double>((double)total, D * 1.25 + 16.0);
+    return VB_OK;
+}
+
 // Feed every input into one fresh table; on overflow (abort flag) start again 4x larger.
 // slot_out (OPK_DICT): one u32 per row over the concatenation of the inputs.
 static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &inputs, int opk, int tx, u64 hint_distinct,
@@ -419,6 +477,7 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
     if (slot_out && any_host) return set_err(VB_ERR_INVALID, "build_table: dictionary inputs must be on the device");
     u32 max_log = std::max<u32>(4, ceil_log2_u64(2 * std::max<u64>(total, 1)));
     if (max_log > MAX_LOG_CAP) return set_err(VB_ERR_TOO_LARGE, "shuffle %llu: %llu rows exceed the device-local limit", (unsigned long long)s->id, (unsigned long long)total);
+    if (!hint_distinct && total > (1ull << 20)) TRY(estimate_distinct(s, inputs, total, &hint_distinct));
     u64 target = hint_distinct ? 2 * hint_distinct : std::min<u64>(2 * std::max<u64>(total, 1), 1ull << 21);
     u32 log_cap = std::min(max_log, std::max<u32>(4, ceil_log2_u64(target)));
 
@@ -786,7 +845,9 @@ static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys,
         if (!rows && !vals && s->agg != VB_AGG_COUNT && n) return set_err(VB_ERR_INVALID, "values required for this aggregator");
         std::vector<AggInput> in(1);
         in[0] = AggInput{rows ? IN_AOS : IN_SOA, rows ? rows : keys, vals, n, loc == VB_HOST ? VB_HOST : VB_DEVICE};
-        TRY(build_table(s, K_HASH_AGG, in, map_opk(s), val_tx(s), s->hint, &m.table, &m.log_cap, &m.n_inserted, nullptr));
+        const u64 hint = s->hint ? s->hint : (s->learned_distinct ? s->learned_distinct + s->learned_distinct / 4 : 0);
+        TRY(build_table(s, K_HASH_AGG, in, map_opk(s), val_tx(s), hint, &m.table, &m.log_cap, &m.n_inserted, nullptr));
+        s->learned_distinct = std::max<u64>(m.n_inserted, 1);
     } else if (n) {
         if (loc == VB_DEVICE_BORROWED) {
             m.rows = rows; m.keys = keys; m.vals = vals; m.owned = false;

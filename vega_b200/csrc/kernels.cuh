@@ -216,6 +216,17 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Tab
     if (tid == 0 && s_inserts) atomicAdd(&ctl->n_inserted, (unsigned long long)s_inserts);
 }
 
+// Strided key sample for the distinct-count estimate that sizes the first table.
+template <int IN>
+__global__ void sample_keys_kernel(const u64 *__restrict__ a, u64 n, u64 stride, u64 *__restrict__ out, u32 m)
+{
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    u64 i = (u64)j * stride;
+    if (i >= n) i = n - 1;
+    out[j] = (IN == IN_AOS) ? a[2 * i] : a[i];
+}
+
 // Read-only lookup used by the join: slot index of `key`, or 0xFFFFFFFF.
 VB_D u32 table_find(const Table &t, u64 key)
 {

@@ -112,12 +112,22 @@ def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, wo
         home = sk.device
         if exchange_device is not None:        # e.g. "cpu" for a gloo group: stage the exchange through the host
             sk, sv = sk.to(exchange_device), sv.to(exchange_device)
+        ev = None
+        if stats is not None and sk.is_cuda:
+            import torch
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         rk, rv, rcounts = all_to_all_v(sk, sv, counts, group)
+        if ev is not None:
+            ev[1].record()
+            ev[1].synchronize()
+            stats["exchange_ms"] = stats.get("exchange_ms", 0.0) + ev[0].elapsed_time(ev[1])
         if exchange_device is not None:
             rk, rv = rk.to(home), rv.to(home)
         if stats is not None:
             stats["sent_rows"] = sum(counts) - counts[rank]
             stats["recv_rows"] = sum(rcounts) - rcounts[rank]
+            stats["exchanges"] = stats.get("exchanges", 0) + 1
         engine.import_(sh, rk, rv, rcounts)
     engine.seal(sh)
     return sh
