@@ -303,3 +303,90 @@ def test_error_conventions(sc):
     sh.free()
     with pytest.raises(vb.VegaB200Error):            # f64 keys are not Hash
         vb.Shuffle(sc, 1, 1, 2, 0, 1)
+
+
+# ---- BASELINE.json configs as (scaled-down) parity cases -------------------------------------
+def test_config1_group_by_1e6_pairs_4_partitions(sc):
+    """configs[0]: examples/group_by.rs shape at 1e6 (u64,u64) pairs, 4 partitions — full size."""
+    import torch
+    n, D = 1_000_000, 10_000
+    rows = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=0, n=n, mode="uniform", n_distinct=D, seed_k=1, seed_v=2)
+    keys, vals = O.gen_uniform(0, n, D, 1, 2)
+    got = gpu_group_parts(sc.make_rdd(rows, 4).group_by_key(4))
+    got = [{k & (2 ** 64 - 1): [x & (2 ** 64 - 1) for x in v] for k, v in d.items()} for d in got]
+    assert got == oracle_group(keys, vals, 4, 4)
+
+
+def test_config5_zipf_skew_reduce_and_group(sc):
+    """configs[4] scaled: Zipf(1.1) keys, 64 reduce partitions.  The hot-key cache path must give
+    exactly the oracle's sums/counts, and group order must survive the skew."""
+    import torch
+    n, D = 2_000_000, 50_000
+    rows = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=0, n=n, mode="zipf", n_distinct=D, seed_k=5, seed_v=2, zipf_s=1.1)
+    host = rows.cpu().numpy().view(np.uint64)
+    keys, vals = host[:, 0].copy(), host[:, 1].copy()
+    top = np.bincount(np.unique(keys, return_inverse=True)[1]).max()
+    assert top > 0.05 * n                      # the generator really is skewed
+    for op in ("sum", "max"):
+        got = gpu_reduce_parts(sc.make_rdd(rows, 8).reduce_by_key(op, 64))
+        got = [{k & (2 ** 64 - 1): v & (2 ** 64 - 1) for k, v in d.items()} for d in got]
+        assert got == oracle_reduce(op, keys, vals, 8, 64)
+    got = gpu_reduce_parts(sc.make_rdd(rows, 8).count_by_key(64))
+    got = [{k & (2 ** 64 - 1): v for k, v in d.items()} for d in got]
+    assert got == oracle_reduce("count", keys, vals, 8, 64)
+    fv = (vals.astype(np.float64) / 2 ** 20)
+    gotf = gpu_reduce_parts(sc.make_rdd((keys, fv), 8).reduce_by_key("sum", 64))
+    wantf = oracle_reduce("sum", keys, fv, 8, 64, "f64")
+    for g, w in zip(gotf, wantf):
+        assert set(g) == set(w)
+        for k in w:
+            assert g[k] == pytest.approx(w[k], rel=1e-6)
+    sub = slice(0, 300_000)
+    assert gpu_group_parts(sc.make_rdd((keys[sub], vals[sub]), 8).group_by_key(64)) == oracle_group(keys[sub], vals[sub], 8, 64)
+
+
+def test_config4_join_unique_keys_scaled(sc):
+    """configs[3] scaled: two RDDs whose keys occur once per side, a known number of shared keys, 8 partitions."""
+    import torch
+    n, shared = 400_000, 8_000
+    a = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    b = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=a, first=0, n=n, mode="unique", rank_base=0)
+    sc.gen_pairs(out_rows=b, first=0, n=n, mode="unique", rank_base=n - shared)
+    k, v, w = sc.make_rdd(a, 8).join(sc.make_rdd(b, 8), 8).collect()
+    assert len(k) == shared and len(np.unique(k)) == shared
+    ha, hb = a.cpu().numpy().view(np.uint64), b.cpu().numpy().view(np.uint64)
+    want = O.join(ha[:, 0].copy(), ha[:, 1].copy(), 8, hb[:, 0].copy(), hb[:, 1].copy(), 8, 8)
+    want_rows = sorted(zip(*[np.concatenate(x).tolist() for x in zip(*want)]))
+    assert sorted(zip(k.view(np.uint64).tolist(), v.view(np.uint64).tolist(), w.view(np.uint64).tolist())) == want_rows
+
+
+def test_config2_full_size_properties(sc):
+    """configs[1] at FULL size (1e9 pairs, 1e6 keys) through size-independent properties: every key of the
+    universe appears exactly once over the 8 partitions, in the partition its hash names; the sums add up
+    to the sum of all values; per-key sums of sampled keys equal a brute-force torch reduction."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2 ** 30:
+        pytest.skip("needs ~20 GB of HBM")
+    n, D = 1_000_000_000, 1_000_000
+    rows = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=0, n=n, mode="uniform", n_distinct=D, seed_k=1, seed_v=2)
+    rdd = sc.make_rdd(rows, 8).reduce_by_key("sum", 8)
+    parts = [rdd.compute(r) for r in range(8)]
+    allk = np.concatenate([p[0] for p in parts]).view(np.uint64)
+    allc = np.concatenate([p[1] for p in parts]).view(np.uint64)
+    assert len(allk) == D and len(np.unique(allk)) == D
+    assert int(allc.sum(dtype=np.uint64)) == int(rows[:, 1].sum().item())
+    universe = np.array([O.lib().vo_splitmix64(int(r) ^ 0xA5A5A5A5A5A5A5A5) for r in range(0, D, 9973)], dtype=np.uint64)
+    assert np.isin(universe, allk).all()
+    for r in (0, 5):
+        kk = parts[r][0].view(np.uint64)
+        assert all(O.get_partition(int(x), 8) == r for x in kk[:: len(kk) // 40])
+    lut = dict(zip(allk.tolist(), allc.tolist()))
+    for key in universe[:3]:
+        brute = int(rows[:, 1][rows[:, 0] == int(np.int64(np.uint64(key).view(np.int64)))].sum().item())
+        assert lut[int(key)] == brute
+    del rows
+    torch.cuda.empty_cache()

@@ -78,6 +78,14 @@ if "sortkv" in ops:
     report("sort_by_key(k,v)", N, 32.0 * N, timed(lambda: run_shuffle(L.VB_AGG_SORT, rows=rows), max(1, args.reps - 1)))
 del rows
 torch.cuda.empty_cache()
+if "zipf" in ops:
+    rows = torch.empty((N, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=0, n=N, mode="zipf", n_distinct=D, seed_k=5, zipf_s=1.1)
+    report("reduce_by_key(sum) zipf(1.1)", N, 16.0 * N + 16.0 * D, timed(lambda: run_shuffle(L.VB_AGG_SUM, rows=rows), args.reps))
+    if "zipfgroup" in ops:
+        report("group_by_key zipf(1.1)", N, 24.0 * N + 16.0 * D, timed(lambda: run_shuffle(L.VB_AGG_GROUP, rows=rows), max(1, args.reps - 1)))
+    del rows
+    torch.cuda.empty_cache()
 if "sort" in ops:
     keys = torch.empty(N, dtype=torch.int64, device="cuda")
     sc.gen_pairs(out_keys=keys, first=0, n=N, mode="unique", rank_base=3)

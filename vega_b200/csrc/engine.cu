@@ -477,8 +477,15 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
     if (slot_out && any_host) return set_err(VB_ERR_INVALID, "build_table: dictionary inputs must be on the device");
     u32 max_log = std::max<u32>(4, ceil_log2_u64(2 * std::max<u64>(total, 1)));
     if (max_log > MAX_LOG_CAP) return set_err(VB_ERR_TOO_LARGE, "shuffle %llu: %llu rows exceed the device-local limit", (unsigned long long)s->id, (unsigned long long)total);
-    if (!hint_distinct && total > (1ull << 20)) TRY(estimate_distinct(s, inputs, total, &hint_distinct));
-    u64 target = hint_distinct ? 2 * hint_distinct : std::min<u64>(2 * std::max<u64>(total, 1), 1ull << 21);
+    bool estimated = false;
+    if (!hint_distinct && total > (1ull << 20)) { TRY(estimate_distinct(s, inputs, total, &hint_distinct)); estimated = true; }
+    // Load factor: <= 0.4 while the table (16 B/slot) still fits comfortably in L2 (<= 64 MB), where a
+    // fuller 4-key bucket costs a second dependent probe (2.9 vs 2.2 ms per 2.5e8 rows at load 0.48 vs
+    // 0.24, profiles/r1_micro_v5_lockstep.log); <= 0.5 for bigger tables, which pay DRAM traffic instead.
+    u64 target = hint_distinct ? (hint_distinct * 5) / 2 : std::min<u64>(2 * std::max<u64>(total, 1), 1ull << 21);
+    if (hint_distinct && target > (1ull << 22)) target = 2 * hint_distinct;
+    // an estimate from a sample is a lower bound under skew: never start a large input below 2^21 slots (32 MB)
+    if (estimated) target = std::max<u64>(target, 1ull << 21);
     u32 log_cap = std::min(max_log, std::max<u32>(4, ceil_log2_u64(target)));
 
     DevBuf ctl(c), stage_a(c), stage_b(c);

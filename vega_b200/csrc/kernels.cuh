@@ -128,24 +128,75 @@ VB_D bool table_resolve(const Table &t, u64 b, Bucket4 bk, u64 key, u64 v, u32 &
     return false;
 }
 
+// ---- per-CTA hot-key cache (skewed keys) -------------------------------------------------------
+// With Zipf(1.1) keys the hottest key owns 12 % of the rows: 1.2e8 REDs to ONE L2 address serialise
+// (measured 104 ms per 1e9 rows vs 10 ms uniform).  Each CTA therefore keeps a small 2-choice cache
+// of (key, partial combiner) in shared memory: rows whose key is cached are combined with a
+// shared-memory atomic and never reach L2; the cache is flushed into the table once, at CTA exit.
+// Keys are cached first-come (hot keys come first with high probability).  For uniformly distributed
+// keys nothing hits, so every CTA measures its hit rate over its first 16 tiles and switches the
+// cache off below 1/16.
+constexpr int HC_SLOTS = 1024;
+#ifndef VB_HC_ENABLE
+#define VB_HC_ENABLE 1
+#endif
+
+template <int OPK>
+VB_D void op_shared(u64 *acc, u64 v)
+{
+    if (OPK == OPK_ADD_U64) atomicAdd((unsigned long long *)acc, (unsigned long long)v);
+    else if (OPK == OPK_COUNT) atomicAdd((unsigned long long *)acc, 1ull);
+    else if (OPK == OPK_ADD_F64) atomicAdd((double *)acc, __longlong_as_double((long long)v));
+    else if (OPK == OPK_MIN_U64) atomicMin((unsigned long long *)acc, (unsigned long long)v);
+    else if (OPK == OPK_MAX_U64) atomicMax((unsigned long long *)acc, (unsigned long long)v);
+}
+
+// 0: not absorbed (row goes to the table); 1: hit an already cached key; 2: claimed an empty cache slot
+template <int OPK>
+VB_D int cache_combine(u64 *hc_keys, u64 *hc_acc, u64 h, u64 key, u64 v)
+{
+    const u32 i1 = (u32)h & (HC_SLOTS - 1), i2 = (u32)(h >> 10) & (HC_SLOTS - 1);
+    const u64 c1 = hc_keys[i1];
+    if (c1 == key) { op_shared<OPK>(&hc_acc[i1], v); return 1; }
+    const u64 c2 = hc_keys[i2];
+    if (c2 == key) { op_shared<OPK>(&hc_acc[i2], v); return 1; }
+    u32 slot;
+    if (c1 == EMPTY_KEY) slot = i1;
+    else if (c2 == EMPTY_KEY) slot = i2;
+    else return 0;
+    const u64 old = atomicCAS((unsigned long long *)&hc_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+    if (old == EMPTY_KEY) { op_shared<OPK>(&hc_acc[slot], v); return 2; }
+    if (old == key) { op_shared<OPK>(&hc_acc[slot], v); return 1; }
+    return 0;
+}
+
 // One pass over n rows.  IN_AOS: a = rows (16 B each).  IN_SOA: a = keys, b = vals (b may be
 // NULL for COUNT/DICT).  IN_TABLE: a/b = keys/accs of a source table of n-1 slots + the special slot.
 // TX: order-preserving value transform applied on load (MIN/MAX over i64/f64).
 template <int IN, int OPK, int TX>
-__global__ void __launch_bounds__(HA_THREADS)
+__global__ void __launch_bounds__(HA_THREADS, 3)   // 3 CTAs/SM measured best (profiles/r1_micro_v4_bucketized.log)
 hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Table t, TableCtl *ctl, u64 max_inserts,
                 u32 *__restrict__ slot_out)
 {
+    constexpr bool CACHE = VB_HC_ENABLE && (OPK != OPK_DICT) && (IN != IN_TABLE);
+    constexpr int OPK_FLUSH = (OPK == OPK_COUNT) ? OPK_ADD_U64 : OPK;      // partial counts are summed
     __shared__ u32 s_inserts;
     __shared__ u32 s_abort;
+    __shared__ u32 s_hits;
+    __shared__ u64 hc_keys[CACHE ? HC_SLOTS : 1];
+    __shared__ u64 hc_acc[CACHE ? HC_SLOTS : 1];
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_inserts = 0; s_abort = 0; }
+    if (tid == 0) { s_inserts = 0; s_abort = 0; s_hits = 0; }
+    if (CACHE)
+        for (u32 i = tid; i < HC_SLOTS; i += HA_THREADS) { hc_keys[i] = EMPTY_KEY; hc_acc[i] = op_identity(OPK); }
     __syncthreads();
     const u64 pol = policy_evict_first();
     const u64 cap = 1ull << t.log_cap;
+    const u32 hshift = 64 - (t.log_cap - 2);
     const u64 n_tiles = (n + HA_TILE - 1) / HA_TILE;
-    u32 my_inserts = 0;
+    u32 my_inserts = 0, my_hits = 0;
     u32 iter = 0;
+    bool use_cache = CACHE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
         const u64 base = tile * HA_TILE;
         u64 k[HA_ROWS], v[HA_ROWS];
@@ -170,33 +221,80 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Tab
                 }
             }
         }
-        // all first probes of the tile in flight before any is consumed
-        u64 hb[HA_ROWS];
-        Bucket4 bk[HA_ROWS];
+        u64 h[HA_ROWS];
 #pragma unroll
         for (int j = 0; j < HA_ROWS; ++j) {
-            hb[j] = home_bucket(k[j], t.log_cap);
-            if (ok[j] && k[j] != EMPTY_KEY) bk[j] = ld_bucket(&t.keys[4 * hb[j]]);
-        }
-#pragma unroll
-        for (int j = 0; j < HA_ROWS; ++j) {
-            if (!ok[j]) continue;
-            const u64 idx = base + (u64)j * HA_THREADS + tid;
-            const u64 val = (TX == TX_NONE) ? v[j] : tx_fwd(v[j], TX);
-            u32 slot = 0;
-            if (k[j] == EMPTY_KEY) {
+            h[j] = slot_hash(k[j]);
+            if (TX != TX_NONE) v[j] = tx_fwd(v[j], TX);
+            if (ok[j] && k[j] == EMPTY_KEY) {           // a real key equal to the empty marker: special slot
                 t.keys[cap] = 1ull;
-                op_red<OPK>(&t.accs[cap], val);
-                slot = (u32)cap;
-            } else if (!table_resolve<OPK>(t, hb[j], bk[j], k[j], val, slot, my_inserts)) {
-                atomicExch(&ctl->abort, 1u);
+                op_red<OPK>(&t.accs[cap], v[j]);
+                if (OPK == OPK_DICT) st_stream_u32(slot_out + base + (u64)j * HA_THREADS + tid, (u32)cap);
+                ok[j] = false;
             }
-            if (OPK == OPK_DICT) st_stream_u32(slot_out + idx, slot);
         }
-        if ((iter & 15u) == 15u) {   // periodic load-factor check; iter is CTA-uniform
+        if (CACHE && use_cache) {
+#pragma unroll
+            for (int j = 0; j < HA_ROWS; ++j) {
+                if (!ok[j]) continue;
+                const int c = cache_combine<OPK>(hc_keys, hc_acc, h[j], k[j], v[j]);
+                if (c) { ok[j] = false; my_hits += (c == 1); }
+            }
+        }
+        // Probe rounds run in lockstep over the HA_ROWS rows of a thread: every round first consumes the
+        // buckets loaded by the previous one, then issues the next probes of all unresolved rows together,
+        // so a tile costs max-over-rows (not sum-over-rows) dependent L2 latencies.
+        Bucket4 bk[HA_ROWS];
+        u64 bidx[HA_ROWS];
+        const u64 nb_mask = (1ull << (t.log_cap - 2)) - 1;
+#pragma unroll
+        for (int j = 0; j < HA_ROWS; ++j) {
+            bidx[j] = h[j] >> hshift;
+            if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
+        }
+        bool pending = true;
+#pragma unroll 1
+        for (u32 probe = 0; pending && probe < HA_MAX_PROBE; ++probe) {
+            pending = false;
+#pragma unroll
+            for (int j = 0; j < HA_ROWS; ++j) {
+                if (!ok[j]) continue;
+                int hit = bucket_find(bk[j], k[j]);
+                if (hit < 0) {
+                    const int e = bucket_find(bk[j], EMPTY_KEY);
+                    if (e < 0) {
+                        bidx[j] = (bidx[j] + 1) & nb_mask;                    // bucket full: next bucket
+                    } else {
+                        const u64 old = atomicCAS((unsigned long long *)&t.keys[4 * bidx[j] + e], (unsigned long long)EMPTY_KEY,
+                                                  (unsigned long long)k[j]);
+                        if (old == EMPTY_KEY) { ++my_inserts; hit = e; }
+                        else if (old == k[j]) hit = e;                        // else: lost the slot, re-read this bucket
+                    }
+                }
+                if (hit >= 0) {
+                    const u64 sl = 4 * bidx[j] + (u64)hit;
+                    op_red<OPK>(&t.accs[sl], v[j]);
+                    if (OPK == OPK_DICT) st_stream_u32(slot_out + base + (u64)j * HA_THREADS + tid, (u32)sl);
+                    ok[j] = false;
+                } else {
+                    pending = true;
+                }
+            }
+            if (pending) {
+#pragma unroll
+                for (int j = 0; j < HA_ROWS; ++j)
+                    if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
+            }
+        }
+        if (pending) atomicExch(&ctl->abort, 1u);   // probe chain longer than HA_MAX_PROBE buckets
+        if ((iter & 15u) == 15u) {   // periodic load-factor check (+ cache verdict); iter is CTA-uniform
             u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
             my_inserts = 0;
             if ((tid & 31u) == 0 && w) atomicAdd(&s_inserts, w);
+            if (CACHE && iter == 15u) {
+                u32 hw = __reduce_add_sync(0xffffffffu, my_hits);
+                if ((tid & 31u) == 0 && hw) atomicAdd(&s_hits, hw);
+            }
             __syncthreads();
             if (tid == 0) {
                 u32 c = s_inserts;
@@ -208,6 +306,17 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Tab
             }
             __syncthreads();
             if (s_abort) return;
+            if (CACHE && iter == 15u && s_hits * 16u < 16u * HA_TILE) use_cache = false;   // < 1/16 of the first 16 tiles
+        }
+    }
+    if (CACHE) {   // flush the cache into the table (merge op)
+        __syncthreads();
+        for (u32 i = tid; i < HC_SLOTS; i += HA_THREADS) {
+            const u64 key = hc_keys[i];
+            if (key == EMPTY_KEY) continue;
+            const u64 hb = home_bucket(key, t.log_cap);
+            u32 slot = 0;
+            if (!table_resolve<OPK_FLUSH>(t, hb, ld_bucket(&t.keys[4 * hb]), key, hc_acc[i], slot, my_inserts)) atomicExch(&ctl->abort, 1u);
         }
     }
     u32 w = __reduce_add_sync(0xffffffffu, my_inserts);

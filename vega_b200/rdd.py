@@ -14,6 +14,7 @@ ParallelCollection::slice, drives map tasks → seal → reduce tasks like the s
 """
 import ctypes
 import itertools
+import weakref
 
 import numpy as np
 
@@ -91,6 +92,7 @@ class Context:
         L.check(self._lib.vb_ctx_create(device, ctypes.byref(h)))
         self._h = h
         self._ids = itertools.count()
+        self._shuffles = weakref.WeakSet()      # live shuffles are freed before the context goes away
         if profile:
             self.set_profile(True)
 
@@ -142,6 +144,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for sh in list(self._shuffles):
+                sh.free()
             self._lib.vb_ctx_destroy(self._h)
             self._h = None
 
@@ -163,6 +167,7 @@ class Shuffle:
         part = L.VB_PART_RANGE if agg == L.VB_AGG_SORT else L.VB_PART_HASH_METRO64
         L.check(self._lib.vb_shuffle_create(sc._h, sc.new_shuffle_id(), n_map, n_reduce, kcode, vcode, agg, part, ctypes.byref(h)))
         self._h = h
+        sc._shuffles.add(self)
         if key_width != 8:
             L.check(self._lib.vb_shuffle_set_key_width(h, key_width))
         if hint:
@@ -224,9 +229,9 @@ class Shuffle:
         return d
 
     def free(self):
-        if self._h:
+        if self._h and self.sc._h:
             self._lib.vb_shuffle_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
