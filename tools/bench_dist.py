@@ -1,0 +1,175 @@
+#!/usr/bin/env python
+"""bench_dist.py — the multi-GPU BASELINE.json configs, one rank per GPU under torchrun:
+
+  zipf   configs[4]: reduce_by_key(sum), rows/GPU Zipf(1.1) pairs over 1e6 keys, 8 map partitions/GPU, 8*N reduce
+  join   configs[3]: join of two RDDs with unique keys (rows/GPU per side), shared keys = rows/50, N map x 8 reduce... (R = max(8, N))
+  group  group_by_key of rows/GPU uniform pairs: raw rows cross NVLink in ONE all-to-all-v (exchange GB/s)
+
+Each line: whole-job rows/s (max over ranks), exchange bytes/time, and a size-independent parity property."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as tdist
+
+import vega_b200 as vb
+from vega_b200 import _lib as L
+from vega_b200 import dist as vdist
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=float, default=1e9, help="rows per GPU")
+ap.add_argument("--distinct", type=float, default=1e6)
+ap.add_argument("--ops", default="zipf,join,group")
+ap.add_argument("--reps", type=int, default=2)
+args = ap.parse_args()
+rank, world, lrank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lrank)
+dev = f"cuda:{lrank}"
+if world > 1:
+    tdist.init_process_group("nccl", device_id=torch.device(dev))
+N, D = int(args.rows), int(args.distinct)
+sc = vb.Context(lrank)
+eng = vdist.CudaEngine(sc)
+stream = sc.stream()
+
+
+def barrier():
+    torch.cuda.synchronize(); sc.synchronize()
+    if world > 1:
+        tdist.barrier()
+    torch.cuda.synchronize()
+
+
+def allmax(x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def allsum(x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
+    return float(t[0])
+
+
+def shuffle(rows, maps_per_rank, R, agg, stats):
+    starts = vb.slice_starts(rows.shape[0], maps_per_rank)
+    lo, _ = vdist.map_block(rank, world, maps_per_rank * world)
+    maps = [(lo + m, rows[int(starts[m]):int(starts[m + 1])], None) for m in range(maps_per_rank)]
+    return vdist.run_shuffle(eng, maps, maps_per_rank * world, R, L.VB_U64, L.VB_U64, agg, rank, world, stats=stats)
+
+
+def timed(fn):
+    fn()
+    best = None
+    for _ in range(args.reps):
+        barrier()
+        t0 = time.perf_counter()
+        out = fn()
+        barrier()
+        dt = allmax(time.perf_counter() - t0)
+        if best is None or dt < best[0]:
+            best = (dt, out)
+    return best
+
+
+def emit(d):
+    if rank == 0:
+        print(json.dumps(d), flush=True)
+
+
+ops = args.ops.split(",")
+if "zipf" in ops:
+    rows = torch.empty((N, 2), dtype=torch.int64, device=dev)
+    sc.gen_pairs(out_rows=rows, first=rank * N, n=N, mode="zipf", n_distinct=D, seed_k=5, seed_v=2, zipf_s=1.1)
+    total_vals = allsum(float(rows[:, 1].sum().item()))
+    R = 8 * world
+
+    def run():
+        st = {}
+        sh = shuffle(rows, 8, R, L.VB_AGG_SUM, st)
+        nk, sm = 0, 0
+        for r in vdist.owned_partitions(rank, world, R):
+            k, c = sh.reduce(r)
+            nk += len(k); sm += int(c.sum(dtype=np.uint64))
+        sh.free()
+        return nk, sm, st
+
+    dt, (nk, sm, st) = timed(run)
+    keys_total, sum_total = allsum(float(nk)), allsum(float(sm))
+    emit({"op": "reduce_by_key(sum) Zipf(1.1) [configs[4]]", "n_gpus": world, "rows_total": N * world, "partitions": R, "s": dt,
+          "rows_per_s": N * world / dt, "distinct_keys_out": int(keys_total), "sum_matches_input": abs(sum_total - total_vals) < 0.5,
+          "exchange_ms": st.get("exchange_ms"), "bytes_sent_per_rank": 16 * st.get("sent_rows", 0),
+          "note": "time includes the D2H read-back of every owned partition"})
+    del rows
+    torch.cuda.empty_cache()
+
+if "group" in ops:
+    n = N // 2            # raw rows cross the fabric and are sorted: keep 2 row buffers + sort scratch within HBM
+    rows = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    sc.gen_pairs(out_rows=rows, first=rank * n, n=n, mode="uniform", n_distinct=D, seed_k=1, seed_v=2)
+    R = max(8, world)
+
+    def run():
+        st = {}
+        sh = shuffle(rows, 8, R, L.VB_AGG_GROUP, st)
+        nk = nv = 0
+        for r in vdist.owned_partitions(rank, world, R):
+            a, b = sh.reduce_size(r)
+            nk += a; nv += b
+        sh.free()
+        return nk, nv, st
+
+    dt, (nk, nv, st) = timed(run)
+    sent = 16 * st.get("sent_rows", 0)
+    xms = st.get("exchange_ms") or 0.0
+    emit({"op": "group_by_key uniform", "n_gpus": world, "rows_total": n * world, "partitions": R, "s": dt, "rows_per_s": n * world / dt,
+          "groups_out": int(allsum(float(nk))), "values_out": int(allsum(float(nv))), "values_match_input": int(allsum(float(nv))) == n * world,
+          "exchange_ms": xms, "bytes_sent_per_rank": sent,
+          "nvlink_all_to_all_GBps_per_rank": (sent / (xms * 1e-3) / 1e9) if xms else None})
+    del rows
+    torch.cuda.empty_cache()
+
+if "join" in ops:
+    n = int(min(N, 5e8 / max(world, 1))) if world > 1 else int(min(N, 6.25e7))
+    shared_total = (n * world) // 50
+    a = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    b = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    sc.gen_pairs(out_rows=a, first=rank * n, n=n, mode="unique", rank_base=0)
+    sc.gen_pairs(out_rows=b, first=rank * n, n=n, mode="unique", rank_base=n * world - shared_total)
+    R = max(8, world)
+
+    def run():
+        st = {}
+        sa = shuffle(a, 1, R, L.VB_AGG_COGROUP, st)
+        sb = shuffle(b, 1, R, L.VB_AGG_COGROUP, st)
+        tot = 0
+        for r in vdist.owned_partitions(rank, world, R):
+            nn = ctypes.c_uint64()
+            L.check(sc._lib.vb_join_size(sa._h, sb._h, r, ctypes.byref(nn)))
+            k, v, w = (torch.empty(nn.value, dtype=torch.int64, device=dev) for _ in range(3))
+            p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
+            L.check(sc._lib.vb_join(sa._h, sb._h, r, p(k), p(v), p(w), L.VB_DEVICE))
+            tot += nn.value
+        sa.free(); sb.free()
+        return tot, st
+
+    dt, (tot, st) = timed(run)
+    out_rows = int(allsum(float(tot)))
+    sent = 16 * st.get("sent_rows", 0)
+    emit({"op": "join unique keys [configs[3]]", "n_gpus": world, "rows_per_side_total": n * world, "partitions": R, "s": dt,
+          "input_rows_per_s": 2 * n * world / dt, "join_rows": out_rows, "join_rows_expected": shared_total,
+          "exchange_ms_both_sides": st.get("exchange_ms"), "bytes_sent_per_rank_last_side": sent})
+sc.close()
+if world > 1:
+    tdist.destroy_process_group()

@@ -557,14 +557,17 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
 struct PassPlan {
     u32 num_parts = 0;
     u64 rows_per_part = 0;
-    size_t hist_bytes() const { return ((size_t)RP_NB * num_parts + 1) * sizeof(u32); }
+    u32 nb = RP_NB;     // bins of this pass
+    size_t hist_bytes() const { return ((size_t)nb * num_parts + 1) * sizeof(u32); }
 };
 
-// (LDM, DGM) combinations the engine uses; anything else is a programming error.
-#define RP_COMBOS(X)                                                         \
-    X(LD_SOA64, DG_BITS) X(LD_AOS64, DG_BITS) X(LD_KEY32_VAL_SOA, DG_BITS) X(LD_KEY32_VAL_AOS, DG_BITS) \
-    X(LD_SOA64, DG_BUCKET) X(LD_TABLE_KV, DG_BUCKET) X(LD_TABLE_KI, DG_BUCKET)                           \
-    X(LD_SOA64, DG_DEST) X(LD_AOS64, DG_DEST) X(LD_TABLE_KV, DG_DEST)
+// (LDM, DGM, BITS) combinations the engine uses; anything else is a programming error.
+// Multisplits (hash(K) % R, destination rank) use 8-bit digits, the LSD sorts 10-bit digits.
+#define RP_COMBOS(X)                                                                                           \
+    X(LD_SOA64, DG_BITS, RP_SORT_BITS) X(LD_AOS64, DG_BITS, RP_SORT_BITS)                                       \
+    X(LD_KEY32_VAL_SOA, DG_BITS, RP_SORT_BITS) X(LD_KEY32_VAL_AOS, DG_BITS, RP_SORT_BITS)                       \
+    X(LD_SOA64, DG_BUCKET, 8) X(LD_TABLE_KV, DG_BUCKET, 8) X(LD_TABLE_KI, DG_BUCKET, 8)                         \
+    X(LD_SOA64, DG_DEST, 8) X(LD_AOS64, DG_DEST, 8) X(LD_TABLE_KV, DG_DEST, 8)
 
 template <typename KeyT, int LDM> constexpr bool rp_key_ok()
 {
@@ -572,33 +575,45 @@ template <typename KeyT, int LDM> constexpr bool rp_key_ok()
 }
 
 template <typename KeyT, bool HAS_VAL>
-static const void *scatter_fn(int ldm, int dgm)
+static const void *scatter_fn(int ldm, int dgm, int bits)
 {
-#define X(L, D) if (ldm == L && dgm == D) { if constexpr (rp_key_ok<KeyT, L>()) return (const void *)rp_scatter_kernel<KeyT, HAS_VAL, L, D>; }
+#define X(L, D, B) if (ldm == L && dgm == D && bits == B) { if constexpr (rp_key_ok<KeyT, L>()) return (const void *)rp_scatter_kernel<KeyT, HAS_VAL, L, D, B>; }
     RP_COMBOS(X)
 #undef X
     return nullptr;
 }
 
 template <typename KeyT>
-static const void *hist_fn(int ldm, int dgm)
+static const void *hist_fn(int ldm, int dgm, int bits)
 {
-#define X(L, D) if (ldm == L && dgm == D) { if constexpr (rp_key_ok<KeyT, L>()) return (const void *)rp_hist_kernel<KeyT, L, D>; }
+#define X(L, D, B) if (ldm == L && dgm == D && bits == B) { if constexpr (rp_key_ok<KeyT, L>()) return (const void *)rp_hist_kernel<KeyT, L, D, B>; }
     RP_COMBOS(X)
 #undef X
     return nullptr;
 }
 
 template <typename KeyT, bool HAS_VAL>
-static PassPlan plan_pass(vb_ctx *c, u64 n)
+static size_t scatter_smem(int bits)
+{
+    return bits == 8 ? rp_scatter_smem<KeyT, HAS_VAL, 8>() : rp_scatter_smem<KeyT, HAS_VAL, RP_SORT_BITS>();
+}
+
+template <typename KeyT, bool HAS_VAL>
+static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
 {
     PassPlan p;
+    p.nb = 1u << bits;
     if (n == 0) return p;
-    // occupancy is the same for every (LDM, DGM) instantiation to within a CTA; use a representative one
-    const void *kern = sizeof(KeyT) == 4 ? scatter_fn<KeyT, HAS_VAL>(LD_KEY32_VAL_SOA, DG_BITS) : scatter_fn<KeyT, HAS_VAL>(LD_SOA64, DG_BITS);
-    size_t smem = rp_scatter_smem<KeyT, HAS_VAL>();
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int occ = occupancy(c, kern, RP_THREADS, smem);
+    // occupancy is the same for every loader/digit instantiation to within a CTA; use a representative one
+    const void *kern = bits == 8 ? scatter_fn<KeyT, HAS_VAL>(LD_SOA64, DG_BUCKET, 8)
+                                 : (sizeof(KeyT) == 4 ? scatter_fn<KeyT, HAS_VAL>(LD_KEY32_VAL_SOA, DG_BITS, bits)
+                                                      : scatter_fn<KeyT, HAS_VAL>(LD_SOA64, DG_BITS, bits));
+    size_t smem = scatter_smem<KeyT, HAS_VAL>(bits);
+    int occ = 2;
+    if (kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        occ = occupancy(c, kern, RPS_THREADS, smem);
+    }
     u64 tiles = (n + RP_TILE - 1) / RP_TILE;
     u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
     u64 tiles_per_part = (tiles + parts - 1) / parts;
@@ -609,20 +624,21 @@ static PassPlan plan_pass(vb_ctx *c, u64 n)
 
 // One stable pass: rows of `ld` (n of them) are written to out_keys/out_vals grouped by digit.
 // d_hist (device, plan.hist_bytes()) afterwards holds the scanned histogram: d_hist[d*num_parts]
-// is the output offset of digit d, d_hist[RP_NB*num_parts] the number of valid rows.
+// is the output offset of digit d, d_hist[nb*num_parts] the number of valid rows.
 template <typename KeyT, bool HAS_VAL>
 static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist,
                       const PassPlan &plan)
 {
     vb_ctx *c = s->ctx;
     if (n == 0 || plan.num_parts == 0) return VB_OK;
-    const void *hk = hist_fn<KeyT>(ld.mode, dg.mode);
-    const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode);
-    if (!hk || !sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d not instantiated", ld.mode, dg.mode);
-    const size_t smem = rp_scatter_smem<KeyT, HAS_VAL>();
+    const int bits = plan.nb == 256 ? 8 : RP_SORT_BITS;
+    const void *hk = hist_fn<KeyT>(ld.mode, dg.mode, bits);
+    const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode, bits);
+    if (!hk || !sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d / %d bits not instantiated", ld.mode, dg.mode, bits);
+    const size_t smem = scatter_smem<KeyT, HAS_VAL>(bits);
     CU(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const u64 tiles_per_part = plan.rows_per_part / RP_TILE;
-    u32 split = (u32)std::max<u64>(1, std::min<u64>(tiles_per_part, ((u64)c->sm_count * 8 + plan.num_parts - 1) / plan.num_parts));
+    u32 split = (u32)std::max<u64>(1, std::min<u64>(tiles_per_part, ((u64)c->sm_count * 6 + plan.num_parts - 1) / plan.num_parts));
     CU(cudaMemsetAsync(d_hist, 0, plan.hist_bytes(), c->stream));
     u64 rows_per_part = plan.rows_per_part;
     u32 num_parts = plan.num_parts;
@@ -631,19 +647,21 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     {
         KLaunch kl(s, K_RP_HIST, n);
         void *args[] = {&ldc, &dgc, &n, &rows_per_part, &d_hist, &num_parts, &split};
-        CU(cudaLaunchKernel(hk, dim3(plan.num_parts * split), dim3(RP_THREADS), args, 0, c->stream));
+        const size_t hsmem = rp_hist_smem(bits);
+        CU(cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        CU(cudaLaunchKernel(hk, dim3(plan.num_parts * split), dim3(RP_THREADS), args, hsmem, c->stream));
         TRY(kl.done("rp_hist_kernel"));
     }
     {
         KLaunch kl(s, K_RP_SCAN);
-        rp_scan_kernel<<<1, 1024, 0, c->stream>>>(d_hist, (u32)RP_NB * plan.num_parts);
+        rp_scan_kernel<<<1, 1024, 0, c->stream>>>(d_hist, plan.nb * plan.num_parts);
         TRY(kl.done("rp_scan_kernel"));
     }
     {
         KLaunch kl(s, K_RP_SCATTER, n);
         const u32 *ch = d_hist;
         void *args[] = {&ldc, &dgc, &n, &rows_per_part, &ch, &num_parts, &out_keys, &out_vals};
-        CU(cudaLaunchKernel(sk, dim3(plan.num_parts), dim3(RP_THREADS), args, smem, c->stream));
+        CU(cudaLaunchKernel(sk, dim3(plan.num_parts), dim3(RPS_THREADS), args, smem, c->stream));
         TRY(kl.done("rp_scatter_kernel"));
     }
     return VB_OK;
@@ -690,7 +708,7 @@ static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, 
     vb_ctx *c = s->ctx;
     bin_off.assign((size_t)nbins + 1, 0);
     if (n == 0) return VB_OK;
-    PassPlan plan = plan_pass<u64, true>(c, n);
+    PassPlan plan = plan_pass<u64, true>(c, n, 8);
     DevBuf hist(c);
     TRY(hist.alloc(plan.hist_bytes()));
     if (nbins <= RP_NB) {
@@ -710,7 +728,7 @@ static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, 
     TRY(fetch_offsets(c, hist.as<u32>(), plan, RP_NB, tmp.data()));
     const u64 nv = tmp[RP_NB];
     if (nv == 0) return VB_OK;
-    PassPlan plan2 = plan_pass<u64, true>(c, nv);
+    PassPlan plan2 = plan_pass<u64, true>(c, nv, 8);
     DevBuf hist2(c);
     TRY(hist2.alloc(plan2.hist_bytes()));
     Loader l2{LD_SOA64, tk.p, tv.p, 0};
@@ -739,8 +757,8 @@ static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, 
 static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32 bits, u32 **out_ids, u64 **out_vals)
 {
     vb_ctx *c = s->ctx;
-    const u32 passes = std::max<u32>(1, (bits + 7) / 8);
-    PassPlan plan = plan_pass<u32, true>(c, n);
+    const u32 passes = std::max<u32>(1, (bits + RP_SORT_BITS - 1) / RP_SORT_BITS);
+    PassPlan plan = plan_pass<u32, true>(c, n, RP_SORT_BITS);
     DevBuf hist(c), ids_b(c), vals_a(c), vals_b(c);
     TRY(hist.alloc(plan.hist_bytes()));
     TRY(ids_b.alloc(n * 4));
@@ -754,8 +772,8 @@ static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32
         else ld = Loader{LD_KEY32_VAL_SOA, src_ids, src_vals, 0};
         Digit dg{};
         dg.mode = DG_BITS;
-        dg.shift = 8 * p;
-        dg.mask = 0xFF;
+        dg.shift = RP_SORT_BITS * p;
+        dg.mask = (1u << RP_SORT_BITS) - 1;
         dg.tx = TX_NONE;
         TRY((radix_pass<u32, true>(s, ld, dg, n, dst_ids, dst_vals, hist.as<u32>(), plan)));
         std::swap(src_ids, dst_ids);
@@ -1112,22 +1130,23 @@ static int seal_sort(vb_shuf *s, const Gathered &g)
     TRY(ka.alloc(n * 8));
     TRY(kb.alloc(n * 8));
     if (has_val) { TRY(va.alloc(n * 8)); TRY(vbuf.alloc(n * 8)); }
-    PassPlan plan = has_val ? plan_pass<u64, true>(c, n) : plan_pass<u64, false>(c, n);
+    PassPlan plan = has_val ? plan_pass<u64, true>(c, n, RP_SORT_BITS) : plan_pass<u64, false>(c, n, RP_SORT_BITS);
     TRY(hist.alloc(plan.hist_bytes()));
     u64 *src_k = nullptr, *src_v = nullptr, *dst_k = ka.as<u64>(), *dst_v = va.as<u64>();
-    for (u32 p = 0; p < 8; ++p) {
+    constexpr u32 SORT_PASSES = (64 + RP_SORT_BITS - 1) / RP_SORT_BITS;
+    for (u32 p = 0; p < SORT_PASSES; ++p) {
         Loader ld;
         if (p == 0) ld = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
         else ld = Loader{LD_SOA64, src_k, has_val ? src_v : nullptr, 0};
         Digit dg{};
-        dg.mode = DG_BITS; dg.shift = 8 * p; dg.mask = 0xFF; dg.tx = tx;
+        dg.mode = DG_BITS; dg.shift = RP_SORT_BITS * p; dg.mask = (1u << RP_SORT_BITS) - 1; dg.tx = tx;
         if (has_val) TRY((radix_pass<u64, true>(s, ld, dg, n, dst_k, dst_v, hist.as<u32>(), plan)));
         else TRY((radix_pass<u64, false>(s, ld, dg, n, dst_k, nullptr, hist.as<u32>(), plan)));
         u64 *nk = (src_k == nullptr) ? kb.as<u64>() : src_k;
         u64 *nv = (src_v == nullptr) ? vbuf.as<u64>() : src_v;
         src_k = dst_k; src_v = dst_v; dst_k = nk; dst_v = nv;
     }
-    // 8 passes: results are in the buffer written by pass 7 == kb / vbuf (ka, kb alternate starting with ka)
+    // results are in the buffer written by the last pass (ka, kb alternate starting with ka)
     DevBuf starts(c);
     TRY(starts.alloc(((size_t)R + 1) * 8));
     {

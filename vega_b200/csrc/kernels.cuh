@@ -359,7 +359,11 @@ constexpr int RP_THREADS = 256;
 constexpr int RP_WARPS = RP_THREADS / 32;
 constexpr int RP_ITEMS = 16;
 constexpr int RP_TILE = RP_THREADS * RP_ITEMS;   // 4096 rows
-constexpr int RP_NB = 256;                       // bins per pass; bin RP_NB = "invalid, drop"
+constexpr int RP_NB = 256;                       // bins of an 8-bit pass (multisplit); bin NB = "invalid, drop"
+constexpr int RPS_THREADS = 512;                 // scatter kernel: 16 warps x 8 items cover the same 4096-row tile with
+constexpr int RPS_WARPS = RPS_THREADS / 32;      // <= 64 registers/thread, so 2 CTAs = 32 warps stay resident per SM
+constexpr int RPS_ITEMS = RP_TILE / RPS_THREADS; // (256 x 16 needed 128 registers: 16 warps/SM, issue slots 32 % busy)
+constexpr int RP_SORT_BITS = 8;                  // digit width of the LSD sort passes; 10-bit digits were measured 2.4x slower per pass (per-tile scan + 4-row write runs), profiles/r1_ops_10bit_digits.jsonl
 
 enum : int { LD_SOA64 = 0, LD_AOS64 = 1, LD_KEY32_VAL_SOA = 2, LD_KEY32_VAL_AOS = 3, LD_TABLE_KV = 4, LD_TABLE_KI = 5 };
 
@@ -442,14 +446,15 @@ VB_D u32 rp_digit(const Digit &dg, KeyT key)
     }
 }
 
-// Lanes of the warp whose 9-bit digit equals mine.  Built from 9 ballots (one per bit) instead of
+// Lanes of the warp whose (BITS+1)-bit digit equals mine.  Built from BITS+1 ballots instead of
 // MATCH.ANY: the hardware match iterates over the distinct values in the warp (~30 for random
 // digits) and dominated both radix kernels (profiles/r1_ncu_rp_match_any.txt: short_scoreboard).
+template <int BITS>
 VB_D u32 warp_match_digit(u32 d)
 {
     u32 peers = 0xffffffffu;
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
+    for (int b = 0; b <= BITS; ++b) {          // BITS digit bits + the "invalid" bit
         const bool bit = (d >> b) & 1u;
         const u32 m = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? m : ~m;
@@ -461,23 +466,49 @@ VB_D u32 warp_match_digit(u32 d)
 // Each part is histogrammed by `split` CTAs (blockIdx.x = part*split + sub) that add their counts
 // with global atomics, so the grid fills the machine even though there are only ~2 parts per SM.
 // hist must be zeroed before the launch.
-template <typename KeyT, int LDM, int DGM>
+// Counting needs no ranking, so instead of a ballot match per item (78 instructions per item,
+// math_pipe_throttle in profiles/r1_ncu_rp_ballot.txt) every LANE keeps private byte counters
+// pc[warp][digit][lane] in shared memory: an item is one LDS.U8 / IADD / STS.U8, no atomics, no votes.
+// A thread adds at most RP_ITEMS per tile, so the bytes are folded into the CTA's u32 histogram
+// every 15 tiles (15 * 16 = 240 <= 255).
+constexpr size_t rp_hist_smem(int bits) { return (size_t)RP_WARPS * ((size_t)1 << bits) * 32; }
+
+template <typename KeyT, int LDM, int DGM, int BITS>
 __global__ void __launch_bounds__(RP_THREADS)
 rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ hist, u32 num_parts, u32 split)
 {
-    __shared__ u32 cnt[RP_WARPS][RP_NB + 1];
+    constexpr int NB = 1 << BITS;
+    extern __shared__ __align__(16) unsigned char pc_raw[];        // [RP_WARPS][NB][32] byte counters
+    __shared__ u32 cta_hist[NB];
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    for (u32 d = tid; d < RP_WARPS * (RP_NB + 1); d += RP_THREADS) (&cnt[0][0])[d] = 0;
+    unsigned char *pc = pc_raw + (size_t)warp * NB * 32;
+    u32 *pcw = (u32 *)pc;
+    for (u32 i = lane; i < NB * 8; i += 32) pcw[i] = 0;
+    for (u32 d = tid; d < NB; d += RP_THREADS) cta_hist[d] = 0;
     __syncthreads();
     const u64 pol = policy_evict_first();
     const u32 part = blockIdx.x / split, sub = blockIdx.x % split;
     const u64 begin = (u64)part * rows_per_part;
     const u64 end = min(n, begin + rows_per_part);
+    auto fold = [&]() {      // warp-local: sum the 32 lane counters of each digit into cta_hist, clear them
+        __syncwarp();
+        for (u32 b = lane; b < NB; b += 32) {
+            u32 s = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const u32 x = pcw[b * 8 + w];
+                pcw[b * 8 + w] = 0;
+                s += (x & 0xFF) + ((x >> 8) & 0xFF) + ((x >> 16) & 0xFF) + (x >> 24);
+            }
+            if (s) atomicAdd(&cta_hist[b], s);
+        }
+        __syncwarp();
+    };
     constexpr int HB = 8;   // items per batch: keeps the u64 instantiation at <= 64 registers
+    u32 tiles_since_fold = 0;
     for (u64 t0 = begin + (u64)sub * RP_TILE; t0 < end; t0 += (u64)split * RP_TILE) {
 #pragma unroll 1
         for (int h = 0; h < RP_ITEMS; h += HB) {
-            u32 dig[HB];
             KeyT key[HB];
             bool ok[HB];
 #pragma unroll
@@ -487,20 +518,19 @@ rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ 
                 ok[i] = (idx < end) && rp_load_key<KeyT, LDM>(ld, idx, key[i], pol);
             }
 #pragma unroll
-            for (int i = 0; i < HB; ++i) dig[i] = ok[i] ? rp_digit<KeyT, DGM>(dg, key[i]) : (u32)RP_NB;
-#pragma unroll
             for (int i = 0; i < HB; ++i) {
-                const u32 peers = warp_match_digit(dig[i]);
-                if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][dig[i]] += __popc(peers);
-                __syncwarp();
+                if (ok[i]) {
+                    const u32 d = rp_digit<KeyT, DGM>(dg, key[i]);
+                    pc[d * 32 + lane] += 1;      // private to this lane: plain read-modify-write
+                }
             }
         }
+        if (++tiles_since_fold == 15) { fold(); tiles_since_fold = 0; }
     }
+    fold();
     __syncthreads();
-    for (u32 d = tid; d < RP_NB; d += RP_THREADS) {
-        u32 s = 0;
-#pragma unroll
-        for (int w = 0; w < RP_WARPS; ++w) s += cnt[w][d];
+    for (u32 d = tid; d < NB; d += RP_THREADS) {
+        const u32 s = cta_hist[d];
         if (s) atomicAdd(&hist[(u64)d * num_parts + part], s);
     }
 }
@@ -544,20 +574,24 @@ __global__ void __launch_bounds__(1024) rp_scan_kernel(u32 *hist, u32 len)
     if (tid == 0) hist[len] = s_total;
 }
 
-template <typename KeyT, bool HAS_VAL, int LDM, int DGM>
-__global__ void __launch_bounds__(RP_THREADS)
+template <int BITS> struct RpTypes { typedef u32 cnt_t; typedef unsigned char dig_t; };
+template <> struct RpTypes<10> { typedef unsigned short cnt_t; typedef unsigned short dig_t; };   // counts <= 4096 fit u16
+
+template <typename KeyT, bool HAS_VAL, int LDM, int DGM, int BITS>
+__global__ void __launch_bounds__(RPS_THREADS, 2)
 rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
                   KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals)
 {
+    constexpr int NB = 1 << BITS;
+    typedef typename RpTypes<BITS>::cnt_t cnt_t;
+    typedef typename RpTypes<BITS>::dig_t dig_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *stage_vals = (u64 *)smem_raw;                                       // [RP_TILE] if HAS_VAL
     KeyT *stage_keys = (KeyT *)(smem_raw + (HAS_VAL ? RP_TILE * 8 : 0));     // [RP_TILE]
-    unsigned char *stage_dig = (unsigned char *)(stage_keys + RP_TILE);      // [RP_TILE]
-    __shared__ u32 cnt[RP_WARPS][RP_NB + 1];
-    __shared__ u32 tot[RP_NB + 1];
-    __shared__ u32 dbase[RP_NB + 2];
-    __shared__ u32 gbase[RP_NB];
-    __shared__ u32 run_off[RP_NB];
+    dig_t *stage_dig = (dig_t *)(stage_keys + RP_TILE);                      // [RP_TILE]
+    __shared__ cnt_t cnt[RPS_WARPS][NB + 1];
+    __shared__ u32 dbase[NB + 2];     // exclusive scan of the per-digit totals of the tile; dbase[NB] = #valid rows
+    __shared__ u32 run_off[NB];       // global output offset of the next row of digit d for this part
 
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const u32 lt = lanemask_lt();
@@ -565,92 +599,94 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
     const u32 part = blockIdx.x;
     const u64 begin = (u64)part * rows_per_part;
     const u64 end = min(n, begin + rows_per_part);
-    for (u32 d = tid; d < RP_NB; d += RP_THREADS) run_off[d] = part_off[(u64)d * num_parts + part];
+    for (u32 d = tid; d < NB; d += RPS_THREADS) run_off[d] = part_off[(u64)d * num_parts + part];
 
-    for (u64 t0 = begin; t0 < end; t0 += RP_TILE) {
-        for (u32 d = tid; d < RP_WARPS * (RP_NB + 1); d += RP_THREADS) (&cnt[0][0])[d] = 0;
-        __syncthreads();   // also orders run_off init / previous tile's smem reads
-
-        KeyT key[RP_ITEMS];
-        u64 val[RP_ITEMS];
-        unsigned short dig[RP_ITEMS], rank[RP_ITEMS];
-        bool ok[RP_ITEMS];
+    // Software pipeline: the loads of tile t+1 are issued right after tile t has been staged into
+    // shared memory (its registers are dead by then), so their DRAM latency overlaps the write-out of
+    // tile t instead of stalling the next iteration (22 % of the stall samples in profiles/r1_ncu_rp_ballot.txt).
+    KeyT key[RPS_ITEMS];
+    u64 val[RPS_ITEMS];
+    bool ok[RPS_ITEMS];
+    auto load_tile = [&](u64 t0) {
 #pragma unroll
-        for (int i = 0; i < RP_ITEMS; ++i) {   // every load of the tile is issued before any is used
-            const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)i * 32 + lane;
+        for (int i = 0; i < RPS_ITEMS; ++i) {
+            const u64 idx = t0 + (u64)warp * (32 * RPS_ITEMS) + (u64)i * 32 + lane;
             key[i] = 0; val[i] = 0;
             ok[i] = (idx < end) && rp_load<KeyT, LDM>(ld, idx, key[i], val[i], pol);
         }
+    };
+    // (u64 key + u64 value needs 32 registers for the tile alone: prefetching spilled under the 64-register cap)
+    constexpr bool PREFETCH = !(sizeof(KeyT) == 8 && HAS_VAL);
+    if (PREFETCH && begin < end) load_tile(begin);
+
+    for (u64 t0 = begin; t0 < end; t0 += RP_TILE) {
+        if (!PREFETCH) load_tile(t0);
+        for (u32 d = tid; d < RPS_WARPS * (NB + 1); d += RPS_THREADS) (&cnt[0][0])[d] = 0;
+        __syncthreads();   // also orders run_off init/update and the previous tile's smem reads
+
+        unsigned short dig[RPS_ITEMS], rank[RPS_ITEMS];
 #pragma unroll
-        for (int i = 0; i < RP_ITEMS; ++i) dig[i] = (unsigned short)(ok[i] ? rp_digit<KeyT, DGM>(dg, key[i]) : (u32)RP_NB);
+        for (int i = 0; i < RPS_ITEMS; ++i) dig[i] = (unsigned short)(ok[i] ? rp_digit<KeyT, DGM>(dg, key[i]) : (u32)NB);
 #pragma unroll
-        for (int i = 0; i < RP_ITEMS; ++i) {
+        for (int i = 0; i < RPS_ITEMS; ++i) {
             const u32 d = dig[i];
-            const u32 peers = warp_match_digit(d);
+            const u32 peers = warp_match_digit<BITS>(d);
             const u32 base = cnt[warp][d];
             __syncwarp();
-            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = base + __popc(peers);
+            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = (cnt_t)(base + __popc(peers));
             __syncwarp();
             rank[i] = (unsigned short)(base + __popc(peers & lt));
         }
         __syncthreads();
-        // per digit: exclusive scan over warps, total
-        for (u32 d = tid; d <= RP_NB; d += RP_THREADS) {
+        // per digit: exclusive scan over warps; the digit's tile total goes to dbase[d] for now
+        for (u32 d = tid; d <= NB; d += RPS_THREADS) {
             u32 s = 0;
 #pragma unroll
-            for (int w = 0; w < RP_WARPS; ++w) { u32 c = cnt[w][d]; cnt[w][d] = s; s += c; }
-            tot[d] = s;
+            for (int w = 0; w < RPS_WARPS; ++w) { u32 c = cnt[w][d]; cnt[w][d] = (cnt_t)s; s += c; }
+            dbase[d] = s;
         }
         __syncthreads();
-        if (warp == 0) {   // exclusive scan of tot[0..RP_NB] → dbase
-            constexpr int PER = (RP_NB + 1 + 31) / 32;
-            u32 loc[PER];
+        if (warp == 0) {   // in-place exclusive scan of dbase[0..NB] (two sweeps over shared memory, no register array)
+            constexpr int PER = (NB + 1 + 31) / 32;
+            const u32 e0 = lane * PER, e1 = min(e0 + PER, (u32)NB + 1);
             u32 s = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                u32 e = lane * PER + j;
-                u32 c = (e <= RP_NB) ? tot[e] : 0u;
-                loc[j] = s; s += c;
-            }
+            for (u32 e = e0; e < e1; ++e) s += dbase[e];
             u32 incl = s;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 u32 t = __shfl_up_sync(0xffffffffu, incl, off);
                 if (lane >= (u32)off) incl += t;
             }
-            const u32 excl = incl - s;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                u32 e = lane * PER + j;
-                if (e <= RP_NB) dbase[e] = excl + loc[j];
-            }
+            u32 run = incl - s;
+            for (u32 e = e0; e < e1; ++e) { const u32 c = dbase[e]; dbase[e] = run; run += c; }
+            if (lane == 31) dbase[NB + 1] = incl;
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < RP_ITEMS; ++i) {
+        for (int i = 0; i < RPS_ITEMS; ++i) {
             const u32 d = dig[i];
             const u32 pos = dbase[d] + cnt[warp][d] + rank[i];
             stage_keys[pos] = key[i];
             if (HAS_VAL) stage_vals[pos] = val[i];
-            stage_dig[pos] = (unsigned char)d;   // d == RP_NB wraps to 0 but lives past n_valid
+            stage_dig[pos] = (dig_t)d;   // rows with d == NB live past n_valid and are never read
         }
-        for (u32 d = tid; d < RP_NB; d += RP_THREADS) gbase[d] = run_off[d] - dbase[d];
+        if (PREFETCH && t0 + RP_TILE < end) load_tile(t0 + RP_TILE);   // in flight during the write-out below
         __syncthreads();
-        const u32 n_valid = dbase[RP_NB];
-        for (u32 p = tid; p < n_valid; p += RP_THREADS) {
+        const u32 n_valid = dbase[NB];
+        for (u32 p = tid; p < n_valid; p += RPS_THREADS) {
             const u32 d = stage_dig[p];
-            const u32 o = gbase[d] + p;
+            const u32 o = run_off[d] + (p - dbase[d]);
             out_keys[o] = stage_keys[p];
             if (HAS_VAL) out_vals[o] = stage_vals[p];
         }
         __syncthreads();
-        for (u32 d = tid; d < RP_NB; d += RP_THREADS) run_off[d] += tot[d];
-        // next iteration's first __syncthreads orders this against its readers
+        for (u32 d = tid; d < NB; d += RPS_THREADS) run_off[d] += dbase[d + 1] - dbase[d];
+        // the next iteration's first __syncthreads orders this against its readers
     }
 }
 
-template <typename KeyT, bool HAS_VAL>
-constexpr size_t rp_scatter_smem() { return (size_t)RP_TILE * ((HAS_VAL ? 8 : 0) + sizeof(KeyT) + 1); }
+template <typename KeyT, bool HAS_VAL, int BITS>
+constexpr size_t rp_scatter_smem() { return (size_t)RP_TILE * ((HAS_VAL ? 8 : 0) + sizeof(KeyT) + sizeof(typename RpTypes<BITS>::dig_t)); }
 
 // ---------------------------------------------------------------------------------------------
 // Generic multi-block exclusive scan (u64), chunk = 4096 elements per CTA
