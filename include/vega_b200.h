@@ -166,6 +166,21 @@ VB_API int32_t vb_join_size(vb_shuf *left, vb_shuf *right, uint32_t reduce_id, u
 VB_API int32_t vb_join(vb_shuf *left, vb_shuf *right, uint32_t reduce_id, void *out_k, void *out_v, void *out_w,
                        int32_t dst_loc);
 
+/* ---- bincode blobs — the payload format of SHUFFLE_CACHE ------------------------
+ * The reference serialises every (map, reduce) bucket with bincode 1.2.1 defaults (src/dependency.rs:213-214:
+ * little-endian, fixed-width integers, u64 length prefixes) and decodes it in the fetcher
+ * (src/shuffle/shuffle_fetcher.rs:85).  These entry points speak that format so GPU results can be
+ * served to, and CPU-produced buckets consumed from, unmodified vega executors:
+ *   Vec<(u64,u64)>      = u64 n | n x (u64 k, u64 c)                       (reduce ops, sort)
+ *   Vec<(u64,Vec<u64>)> = u64 n | n x (u64 k, u64 len, len x u64)          (group ops)
+ * vb_shuffle_reduce_blob encodes one sealed reduce partition; vb_shuffle_map_blob submits one
+ * map-side-COMBINED bucket as the output of map task `map_id` (combiners are merged with
+ * merge_combiners, so partial counts are summed).  A blob whose length field disagrees with its
+ * size is rejected with VB_ERR_INVALID (the reference's DeserializationError).                   */
+VB_API int32_t vb_shuffle_reduce_blob_size(vb_shuf *s, uint32_t reduce_id, uint64_t *n_bytes);
+VB_API int32_t vb_shuffle_reduce_blob(vb_shuf *s, uint32_t reduce_id, void *out_blob, int32_t dst_loc);
+VB_API int32_t vb_shuffle_map_blob(vb_shuf *s, uint32_t map_id, const void *blob, uint64_t n_bytes, int32_t src_loc);
+
 VB_API int32_t vb_shuffle_free(vb_shuf *s);
 VB_API int32_t vb_shuffle_stats(vb_shuf *s, vb_stats *out);
 VB_API const char *vb_last_error(void);

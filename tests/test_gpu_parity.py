@@ -390,3 +390,74 @@ def test_config2_full_size_properties(sc):
         assert lut[int(key)] == brute
     del rows
     torch.cuda.empty_cache()
+
+
+def test_cpp_host_mirror_examples_run():
+    """examples/group_by.cpp and examples/join.cpp are the reference's examples/group_by.rs and
+    examples/join.rs over include/vega_b200.hpp (same data); they exit 0 only on the expected result."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for exe, needle in (("group_by", "[1, 2, 3, 4, 5, 6, 7, 8]"), ("join", "(3, (C2, (E,F)))")):
+        path = os.path.join(root, "examples", "_build", exe)
+        if not os.path.exists(path):
+            pytest.skip("examples not built (run __graft_entry__.build())")
+        out = subprocess.run([path], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        assert needle in out.stdout, out.stdout
+
+
+# ---- SURVEY §8(f) N1: bincode blobs ------------------------------------------------------------
+def test_bincode_blobs_encode_decode(sc):
+    from oracle import bincode_ref as B
+    rng = np.random.default_rng(77)
+    keys, vals = rand_pairs(rng, 40_000, 900)
+    # encode: reduce partition → Vec<(u64,u64)> bytes == oracle's encoding of the same rows
+    rdd = sc.parallelize((keys, vals), 3).reduce_by_key("sum", 4)
+    sh = rdd._run()
+    for r in range(4):
+        k, c = sh.reduce(r)
+        blob = sh.reduce_blob(r)
+        assert blob == B.encode_pairs(list(zip(k.tolist(), c.tolist())))
+        assert dict(B.decode_pairs(blob)) == oracle_reduce("sum", keys, vals, 3, 4)[r]
+    # encode: group partition → Vec<(u64,Vec<u64>)>
+    g = sc.parallelize((keys, vals), 3).group_by_key(2)
+    gsh = g._run()
+    for r in range(2):
+        k, o, v = gsh.reduce(r)
+        want = [(int(k[i]), v[int(o[i]):int(o[i + 1])].tolist()) for i in range(len(k))]
+        assert gsh.reduce_blob(r) == B.encode_groups(want)
+    # decode: CPU-produced map-side-combined buckets (the oracle's map outputs) consumed as map tasks
+    for op, agg in (("sum", 1), ("count", 4), ("max", 3)):
+        sh2 = vb.Shuffle(sc, 3, 1, 0, 0, agg)
+        starts = vb.slice_starts(len(keys), 3)
+        for m in range(3):
+            part = O.shuffle(op, keys[starts[m]:starts[m + 1]], vals[starts[m]:starts[m + 1]], 1, 1)[0]
+            sh2.map_blob(m, B.encode_pairs(list(zip(part["keys"].tolist(), part["combined"].tolist()))))
+        sh2.seal()
+        k, c = sh2.reduce(0)
+        assert dict(zip(k.tolist(), c.tolist())) == oracle_reduce(op, keys, vals, 3, 1)[0]
+        sh2.free()
+    sh3 = vb.Shuffle(sc, 2, 2, 0, 0, 0)
+    half = len(keys) // 2
+    for m, sl in enumerate((slice(0, half), slice(half, None))):
+        part = oracle_group(keys[sl], vals[sl], 1, 1)[0]
+        sh3.map_blob(m, B.encode_groups(list(part.items())))
+    sh3.seal()
+    got = {}
+    for r in range(2):
+        k, o, v = sh3.reduce(r)
+        got.update({int(k[i]): v[int(o[i]):int(o[i + 1])].tolist() for i in range(len(k))})
+    want = {}
+    for d in oracle_group(keys, vals, 2, 2):
+        want.update(d)
+    # a blob lists each key's values in the map task's encounter order, so the reference's group order survives
+    assert got == want
+    sh3.free()
+    # corrupted payloads are rejected, not crashed on (shuffle_fetcher.rs:168-185)
+    bad = vb.Shuffle(sc, 1, 1, 0, 0, 1)
+    for blob in (b"\x05" + b"\x00" * 7, b"\x01" + b"\x00" * 15, b"\x00" * 7):
+        with pytest.raises(vb.VegaB200Error) as e:
+            bad.map_blob(0, blob)
+        assert e.value.code == -1
+    bad.free()

@@ -212,3 +212,20 @@ def test_generator_matches_numpy():
         rank = sm(np.uint64(1) + i) % np.uint64(37)
         assert (k == sm(rank ^ np.uint64(0xA5A5A5A5A5A5A5A5))).all()
         assert (v == (sm(np.uint64(2) + i) & np.uint64(0xFFFFF))).all()
+
+
+# -- bincode blobs: the reference's only fixture is a round trip -------------
+def test_bincode_reference_fixture_round_trip():
+    from oracle import bincode_ref as B
+    # src/shuffle/shuffle_fetcher.rs:154-166: vec![(0i32, "example data")] at key (11000, 0, 11001)
+    blob = B.encode_i32_string_vec([(0, "example data")])
+    assert len(blob) == 8 + 4 + 8 + 12 and blob[:8] == (1).to_bytes(8, "little")
+    assert B.decode_i32_string_vec(blob) == [(0, "example data")]
+    # :168-185 fetch_failure: a payload of another type does not decode
+    with pytest.raises(Exception):
+        B.decode_i32_string_vec(b"\x0e\x00\x00\x00\x00\x00\x00\x00corrupted data")
+    pairs = [(1, 2), (2 ** 64 - 1, 0)]
+    assert B.decode_pairs(B.encode_pairs(pairs)) == pairs
+    groups = [(7, [1, 2, 3]), (9, [])]
+    assert B.decode_groups(B.encode_groups(groups)) == groups
+    assert len(B.encode_groups(groups)) == 8 + 16 * 2 + 8 * 3

@@ -62,6 +62,9 @@ SYMBOLS = {
     "vb_shuffle_reduce": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _i32]),
     "vb_join_size": (_i32, [_vp, _vp, _u32, _pu64]),
     "vb_join": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _i32]),
+    "vb_shuffle_reduce_blob_size": (_i32, [_vp, _u32, _pu64]),
+    "vb_shuffle_reduce_blob": (_i32, [_vp, _u32, _vp, _i32]),
+    "vb_shuffle_map_blob": (_i32, [_vp, _u32, _vp, _u64, _i32]),
     "vb_shuffle_free": (_i32, [_vp]),
     "vb_shuffle_stats": (_i32, [_vp, ctypes.POINTER(vb_stats)]),
     "vb_shuffle_kernel_time": (_i32, [_vp, _i32, ctypes.POINTER(_dbl), _pu64]),

@@ -848,7 +848,7 @@ static void free_map(vb_shuf *s, MapOut &m)
     m = MapOut();
 }
 
-static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys, const u64 *vals, u64 n, int loc)
+static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys, const u64 *vals, u64 n, int loc, bool combined = false)
 {
     if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
     if (map_id >= s->n_map) return set_err(VB_ERR_INVALID, "map_id %u >= n_map %u", map_id, s->n_map);
@@ -871,7 +871,8 @@ static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys,
         std::vector<AggInput> in(1);
         in[0] = AggInput{rows ? IN_AOS : IN_SOA, rows ? rows : keys, vals, n, loc == VB_HOST ? VB_HOST : VB_DEVICE};
         const u64 hint = s->hint ? s->hint : (s->learned_distinct ? s->learned_distinct + s->learned_distinct / 4 : 0);
-        TRY(build_table(s, K_HASH_AGG, in, map_opk(s), val_tx(s), hint, &m.table, &m.log_cap, &m.n_inserted, nullptr));
+        // a map-side-combined bucket carries combiners, merged with merge_combiners (partial counts are summed)
+        TRY(build_table(s, K_HASH_AGG, in, combined ? merge_opk(s) : map_opk(s), val_tx(s), hint, &m.table, &m.log_cap, &m.n_inserted, nullptr));
         s->learned_distinct = std::max<u64>(m.n_inserted, 1);
     } else if (n) {
         if (loc == VB_DEVICE_BORROWED) {
@@ -1369,6 +1370,95 @@ extern "C" int32_t vb_shuffle_reduce(vb_shuf *s, uint32_t r, void *out_keys, voi
     }
     CU(cudaStreamSynchronize(c->stream));
     return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bincode blobs (N1)
+// ---------------------------------------------------------------------------------------------
+static u64 blob_bytes(const vb_shuf *s, u32 r)
+{
+    const u64 nk = s->bucket_off[r + 1] - s->bucket_off[r];
+    if (is_group_op(s->agg)) return 8 + 16 * nk + 8 * (s->val_off[r + 1] - s->val_off[r]);
+    return 8 + 16 * nk;
+}
+
+extern "C" int32_t vb_shuffle_reduce_blob_size(vb_shuf *s, uint32_t r, uint64_t *n_bytes)
+{
+    if (!s || !n_bytes) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (r >= s->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", r, s->n_reduce);
+    TRY(wait_sealed(s));
+    *n_bytes = blob_bytes(s, r);
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_reduce_blob(vb_shuf *s, uint32_t r, void *out_blob, int32_t dst_loc)
+{
+    if (!s || !out_blob) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (r >= s->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", r, s->n_reduce);
+    if (dst_loc != VB_HOST && dst_loc != VB_DEVICE) return set_err(VB_ERR_INVALID, "bad dst_loc");
+    TRY(wait_sealed(s));
+    vb_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const u64 bytes = blob_bytes(s, r);
+    const u64 b0 = s->bucket_off[r], nk = s->bucket_off[r + 1] - b0;
+    DevBuf tmp(c);
+    u64 *dst = (u64 *)out_blob;
+    if (dst_loc == VB_HOST) { TRY(tmp.alloc(bytes)); dst = tmp.as<u64>(); }
+    const unsigned grid = (unsigned)std::min<u64>(std::max<u64>(1, (std::max(nk, s->val_off[r + 1] - s->val_off[r]) + 255) / 256), (u64)c->sm_count * 8);
+    {
+        KLaunch kl(s, K_MISC);
+        if (is_group_op(s->agg)) {
+            if (nk) blob_group_kernel<<<grid, 256, 0, c->stream>>>(s->res_keys + b0, s->res_offs + b0, nk, s->res_vals, dst);
+            else CU(cudaMemsetAsync(dst, 0, 8, c->stream));
+        } else {
+            if (nk) blob_pairs_kernel<<<grid, 256, 0, c->stream>>>(s->res_keys + b0, s->res_comb ? s->res_comb + b0 : nullptr, nk, dst);
+            else CU(cudaMemsetAsync(dst, 0, 8, c->stream));
+        }
+        TRY(kl.done("blob kernel"));
+    }
+    if (dst_loc == VB_HOST) TRY(copy_out(s, out_blob, dst, bytes, VB_HOST));
+    CU(cudaStreamSynchronize(c->stream));
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_map_blob(vb_shuf *s, uint32_t map_id, const void *blob, uint64_t n_bytes, int32_t src_loc)
+{
+    if (!s || !blob) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (src_loc < VB_HOST || src_loc > VB_DEVICE_BORROWED) return set_err(VB_ERR_INVALID, "bad src_loc");
+    if (s->agg == VB_AGG_SORT) return set_err(VB_ERR_UNSUPPORTED, "sort_by_key takes rows, not combined buckets");
+    if (n_bytes < 8 || (n_bytes & 7)) return set_err(VB_ERR_INVALID, "corrupted blob: %llu bytes", (unsigned long long)n_bytes);
+    vb_ctx *c = s->ctx;
+    // the whole blob on the host: CPU-produced buckets arrive there anyway, and the record structure of
+    // Vec<(K,Vec<V>)> is a linked list (each record's position depends on the previous lengths)
+    std::vector<u64> host;
+    const u64 *w = (const u64 *)blob;
+    if (src_loc != VB_HOST) {
+        host.resize(n_bytes / 8);
+        std::lock_guard<std::mutex> lk(c->mu);
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemcpyAsync(host.data(), blob, n_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        w = host.data();
+    }
+    const u64 words = n_bytes / 8, n = w[0];
+    if (!is_group_op(s->agg)) {
+        if (n > (words - 1) / 2 || words != 1 + 2 * n) return set_err(VB_ERR_INVALID, "corrupted blob: %llu records in %llu bytes", (unsigned long long)n, (unsigned long long)n_bytes);
+        std::vector<u64> k(n), v(n);
+        for (u64 i = 0; i < n; ++i) { k[i] = w[1 + 2 * i]; v[i] = w[2 + 2 * i]; }
+        return shuffle_map(s, map_id, nullptr, k.data(), v.data(), n, VB_HOST, /*combined=*/true);
+    }
+    std::vector<u64> k, v;
+    u64 pos = 1;
+    for (u64 i = 0; i < n; ++i) {
+        if (pos + 2 > words) return set_err(VB_ERR_INVALID, "corrupted blob: record %llu runs past the end", (unsigned long long)i);
+        const u64 key = w[pos], len = w[pos + 1];
+        if (len > words - pos - 2) return set_err(VB_ERR_INVALID, "corrupted blob: record %llu has length %llu", (unsigned long long)i, (unsigned long long)len);
+        for (u64 j = 0; j < len; ++j) { k.push_back(key); v.push_back(w[pos + 2 + j]); }
+        pos += 2 + len;
+    }
+    if (pos != words) return set_err(VB_ERR_INVALID, "corrupted blob: %llu trailing bytes", (unsigned long long)((words - pos) * 8));
+    return shuffle_map(s, map_id, nullptr, k.data(), v.data(), k.size(), VB_HOST, false);
 }
 
 // ---------------------------------------------------------------------------------------------

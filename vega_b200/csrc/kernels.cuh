@@ -856,6 +856,44 @@ __global__ void join_expand_kernel(const u64 *__restrict__ pos /*[nl] exclusive*
 }
 
 // ---------------------------------------------------------------------------------------------
+// bincode 1.2.1 blob codec: pure byte shuffling, HBM-bound
+// ---------------------------------------------------------------------------------------------
+// Vec<(u64,u64)>: out = u64 n | n x (k, c)
+__global__ void blob_pairs_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ comb, u64 n, u64 *__restrict__ out)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    if (i == 0) out[0] = n;
+    for (; i < n; i += stride) {
+        out[1 + 2 * i] = keys[i];
+        out[2 + 2 * i] = comb ? comb[i] : 0ull;
+    }
+}
+
+// Vec<(u64,Vec<u64>)>: record i starts at word 1 + 2 i + offs[i] - base: (k, len, values...)
+__global__ void blob_group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ offs /*[nk+1], absolute*/, u64 nk,
+                                  const u64 *__restrict__ vals /*absolute index*/, u64 *__restrict__ out)
+{
+    const u64 base = offs[0], nv = offs[nk] - base;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    if (t == 0) out[0] = nk;
+    for (u64 i = t; i < nk; i += stride) {
+        const u64 w = 1 + 2 * i + (offs[i] - base);
+        out[w] = keys[i];
+        out[w + 1] = offs[i + 1] - offs[i];
+    }
+    for (u64 j = t; j < nv; j += stride) {      // value j belongs to the key i with offs[i] <= base + j < offs[i+1]
+        u64 lo = 0, hi = nk;
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if (offs[mid] - base <= j) lo = mid; else hi = mid;
+        }
+        out[1 + 2 * (lo + 1) + j] = vals[base + j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // sort_by_key partition cuts: start of partition p = floor(p*n/R) moved past equal keys
 // ---------------------------------------------------------------------------------------------
 __global__ void sort_cuts_kernel(const u64 *__restrict__ keys, u64 n, u32 n_parts, u64 *__restrict__ starts)

@@ -216,6 +216,19 @@ class Shuffle:
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         L.check(self._lib.vb_shuffle_reduce(self._h, r, p(out_keys), p(out_comb), p(out_offs), p(out_vals), L.VB_DEVICE))
 
+    def reduce_blob(self, r):
+        """Reduce partition r as the bincode 1.2.1 blob vega stores in SHUFFLE_CACHE (bytes)."""
+        n = ctypes.c_uint64()
+        L.check(self._lib.vb_shuffle_reduce_blob_size(self._h, r, ctypes.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        L.check(self._lib.vb_shuffle_reduce_blob(self._h, r, buf.ctypes.data_as(ctypes.c_void_p), L.VB_HOST))
+        return buf.tobytes()
+
+    def map_blob(self, map_id, blob):
+        """Submit one map-side-combined bucket (bincode blob, bytes) as the output of map task `map_id`."""
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        L.check(self._lib.vb_shuffle_map_blob(self._h, map_id, buf.ctypes.data_as(ctypes.c_void_p), len(buf), L.VB_HOST))
+
     def stats(self):
         st = L.vb_stats()
         L.check(self._lib.vb_shuffle_stats(self._h, ctypes.byref(st)))
