@@ -363,7 +363,8 @@ constexpr int RP_NB = 256;                       // bins of an 8-bit pass (multi
 constexpr int RPS_THREADS = 512;                 // scatter kernel: 16 warps x 8 items cover the same 4096-row tile with
 constexpr int RPS_WARPS = RPS_THREADS / 32;      // <= 64 registers/thread, so 2 CTAs = 32 warps stay resident per SM
 constexpr int RPS_ITEMS = RP_TILE / RPS_THREADS; // (256 x 16 needed 128 registers: 16 warps/SM, issue slots 32 % busy)
-constexpr int RP_SORT_BITS = 8;                  // digit width of the LSD sort passes; 10-bit digits were measured 2.4x slower per pass (per-tile scan + 4-row write runs), profiles/r1_ops_10bit_digits.jsonl
+constexpr int RP_SORT_BITS = 8;                  // digit width of the LSD sort passes; a 10-bit variant was measured 2.4x slower per pass
+                                                 // (per-tile scan over 1025 bins + 4-row write runs), profiles/r1_ops_10bit_digits.jsonl
 
 enum : int { LD_SOA64 = 0, LD_AOS64 = 1, LD_KEY32_VAL_SOA = 2, LD_KEY32_VAL_AOS = 3, LD_TABLE_KV = 4, LD_TABLE_KI = 5 };
 
@@ -574,24 +575,31 @@ __global__ void __launch_bounds__(1024) rp_scan_kernel(u32 *hist, u32 len)
     if (tid == 0) hist[len] = s_total;
 }
 
-template <int BITS> struct RpTypes { typedef u32 cnt_t; typedef unsigned char dig_t; };
-template <> struct RpTypes<10> { typedef unsigned short cnt_t; typedef unsigned short dig_t; };   // counts <= 4096 fit u16
-
+// One stable scatter pass.  Per 4096-row tile: rank every row inside its warp by digit (ballots), scan
+// the warp counts across the CTA, stage the tile in shared memory in output order together with each
+// row's GLOBAL output index, then write it out with consecutive threads touching consecutive staged
+// rows (runs of ~16 rows per digit → coalesced 64-128 B segments).  5 barriers per tile; the counters
+// for the next tile are cleared and its loads are in flight while the current tile is written out.
 template <typename KeyT, bool HAS_VAL, int LDM, int DGM, int BITS>
 __global__ void __launch_bounds__(RPS_THREADS, 2)
 rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
                   KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals)
 {
     constexpr int NB = 1 << BITS;
-    typedef typename RpTypes<BITS>::cnt_t cnt_t;
-    typedef typename RpTypes<BITS>::dig_t dig_t;
+    static_assert(NB + 1 <= RPS_THREADS, "one thread per digit in the tile scan");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *stage_vals = (u64 *)smem_raw;                                       // [RP_TILE] if HAS_VAL
     KeyT *stage_keys = (KeyT *)(smem_raw + (HAS_VAL ? RP_TILE * 8 : 0));     // [RP_TILE]
-    dig_t *stage_dig = (dig_t *)(stage_keys + RP_TILE);                      // [RP_TILE]
-    __shared__ cnt_t cnt[RPS_WARPS][NB + 1];
-    __shared__ u32 dbase[NB + 2];     // exclusive scan of the per-digit totals of the tile; dbase[NB] = #valid rows
-    __shared__ u32 run_off[NB];       // global output offset of the next row of digit d for this part
+    // the widest rows (u64 key + u64 value) stage the 1-byte digit and look the offset up at write-out
+    // instead of staging a 4-byte output index: 18 % faster for them, 2-4 % slower for the others (A/B on B200)
+    constexpr bool STAGE_IDX = !(sizeof(KeyT) == 8 && HAS_VAL);
+    u32 *stage_out = (u32 *)(stage_keys + RP_TILE);                          // [RP_TILE] global output index (STAGE_IDX)
+    unsigned char *stage_dig = (unsigned char *)(stage_keys + RP_TILE);      // [RP_TILE] digit (!STAGE_IDX)
+    __shared__ u32 cnt[RPS_WARPS][NB + 1];   // per warp: count, then exclusive prefix over warps
+    __shared__ u32 dbase[NB + 1];            // tile-local start of digit d; dbase[NB] = #valid rows of the tile
+    __shared__ u32 gbase[NB + 1];            // run_off[d] - dbase[d]: staged position p of digit d goes to gbase[d] + p
+    __shared__ u32 run_off[NB];              // global output offset of the next row of digit d for this part
+    __shared__ u32 wtot[RPS_WARPS];
 
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const u32 lt = lanemask_lt();
@@ -600,16 +608,14 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
     const u64 begin = (u64)part * rows_per_part;
     const u64 end = min(n, begin + rows_per_part);
     for (u32 d = tid; d < NB; d += RPS_THREADS) run_off[d] = part_off[(u64)d * num_parts + part];
+    for (u32 d = tid; d < RPS_WARPS * (NB + 1); d += RPS_THREADS) (&cnt[0][0])[d] = 0;
 
-    // Software pipeline: the loads of tile t+1 are issued right after tile t has been staged into
-    // shared memory (its registers are dead by then), so their DRAM latency overlaps the write-out of
-    // tile t instead of stalling the next iteration (22 % of the stall samples in profiles/r1_ncu_rp_ballot.txt).
     KeyT key[RPS_ITEMS];
     u64 val[RPS_ITEMS];
     bool ok[RPS_ITEMS];
     auto load_tile = [&](u64 t0) {
 #pragma unroll
-        for (int i = 0; i < RPS_ITEMS; ++i) {
+        for (int i = 0; i < RPS_ITEMS; ++i) {   // every load of the tile is issued before any is used
             const u64 idx = t0 + (u64)warp * (32 * RPS_ITEMS) + (u64)i * 32 + lane;
             key[i] = 0; val[i] = 0;
             ok[i] = (idx < end) && rp_load<KeyT, LDM>(ld, idx, key[i], val[i], pol);
@@ -618,12 +624,10 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
     // (u64 key + u64 value needs 32 registers for the tile alone: prefetching spilled under the 64-register cap)
     constexpr bool PREFETCH = !(sizeof(KeyT) == 8 && HAS_VAL);
     if (PREFETCH && begin < end) load_tile(begin);
+    __syncthreads();
 
     for (u64 t0 = begin; t0 < end; t0 += RP_TILE) {
         if (!PREFETCH) load_tile(t0);
-        for (u32 d = tid; d < RPS_WARPS * (NB + 1); d += RPS_THREADS) (&cnt[0][0])[d] = 0;
-        __syncthreads();   // also orders run_off init/update and the previous tile's smem reads
-
         unsigned short dig[RPS_ITEMS], rank[RPS_ITEMS];
 #pragma unroll
         for (int i = 0; i < RPS_ITEMS; ++i) dig[i] = (unsigned short)(ok[i] ? rp_digit<KeyT, DGM>(dg, key[i]) : (u32)NB);
@@ -633,60 +637,62 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
             const u32 peers = warp_match_digit<BITS>(d);
             const u32 base = cnt[warp][d];
             __syncwarp();
-            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = (cnt_t)(base + __popc(peers));
+            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = base + __popc(peers);
             __syncwarp();
             rank[i] = (unsigned short)(base + __popc(peers & lt));
         }
-        __syncthreads();
-        // per digit: exclusive scan over warps; the digit's tile total goes to dbase[d] for now
-        for (u32 d = tid; d <= NB; d += RPS_THREADS) {
-            u32 s = 0;
+        __syncthreads();                                                        // B1: warp counts complete
+        // thread d: exclusive scan of digit d over the warps, then a block-wide exclusive scan over the digits
+        u32 total = 0;
+        if (tid <= NB) {
 #pragma unroll
-            for (int w = 0; w < RPS_WARPS; ++w) { u32 c = cnt[w][d]; cnt[w][d] = (cnt_t)s; s += c; }
-            dbase[d] = s;
+            for (int w = 0; w < RPS_WARPS; ++w) { const u32 c = cnt[w][tid]; cnt[w][tid] = total; total += c; }
         }
-        __syncthreads();
-        if (warp == 0) {   // in-place exclusive scan of dbase[0..NB] (two sweeps over shared memory, no register array)
-            constexpr int PER = (NB + 1 + 31) / 32;
-            const u32 e0 = lane * PER, e1 = min(e0 + PER, (u32)NB + 1);
-            u32 s = 0;
-            for (u32 e = e0; e < e1; ++e) s += dbase[e];
-            u32 incl = s;
+        u32 incl = total;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                u32 t = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= (u32)off) incl += t;
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (u32)off) incl += t;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();                                                        // B2: warp totals visible
+        if (tid <= NB) {
+            u32 excl = incl - total;
+            for (u32 w = 0; w < warp; ++w) excl += wtot[w];
+            dbase[tid] = excl;
+            if (tid < NB) {
+                const u32 ro = run_off[tid];
+                gbase[tid] = ro - excl;
+                run_off[tid] = ro + total;
             }
-            u32 run = incl - s;
-            for (u32 e = e0; e < e1; ++e) { const u32 c = dbase[e]; dbase[e] = run; run += c; }
-            if (lane == 31) dbase[NB + 1] = incl;
         }
-        __syncthreads();
+        __syncthreads();                                                        // B3: dbase / gbase visible
 #pragma unroll
         for (int i = 0; i < RPS_ITEMS; ++i) {
             const u32 d = dig[i];
             const u32 pos = dbase[d] + cnt[warp][d] + rank[i];
             stage_keys[pos] = key[i];
             if (HAS_VAL) stage_vals[pos] = val[i];
-            stage_dig[pos] = (dig_t)d;   // rows with d == NB live past n_valid and are never read
+            if (d < NB) {                                   // rows with d == NB (invalid) sit past n_valid
+                if (STAGE_IDX) stage_out[pos] = gbase[d] + pos;
+                else stage_dig[pos] = (unsigned char)d;
+            }
         }
-        if (PREFETCH && t0 + RP_TILE < end) load_tile(t0 + RP_TILE);   // in flight during the write-out below
-        __syncthreads();
+        if (PREFETCH && t0 + RP_TILE < end) load_tile(t0 + RP_TILE);             // in flight during the write-out below
+        __syncthreads();                                                        // B4: tile staged, cnt free
+        for (u32 d = tid; d < RPS_WARPS * (NB + 1); d += RPS_THREADS) (&cnt[0][0])[d] = 0;
         const u32 n_valid = dbase[NB];
         for (u32 p = tid; p < n_valid; p += RPS_THREADS) {
-            const u32 d = stage_dig[p];
-            const u32 o = run_off[d] + (p - dbase[d]);
+            const u32 o = STAGE_IDX ? stage_out[p] : gbase[stage_dig[p]] + p;
             out_keys[o] = stage_keys[p];
             if (HAS_VAL) out_vals[o] = stage_vals[p];
         }
-        __syncthreads();
-        for (u32 d = tid; d < NB; d += RPS_THREADS) run_off[d] += dbase[d + 1] - dbase[d];
-        // the next iteration's first __syncthreads orders this against its readers
+        __syncthreads();                                                        // B5: staging buffers and cnt reusable
     }
 }
 
 template <typename KeyT, bool HAS_VAL, int BITS>
-constexpr size_t rp_scatter_smem() { return (size_t)RP_TILE * ((HAS_VAL ? 8 : 0) + sizeof(KeyT) + sizeof(typename RpTypes<BITS>::dig_t)); }
+constexpr size_t rp_scatter_smem() { return (size_t)RP_TILE * ((HAS_VAL ? 8 : 0) + sizeof(KeyT) + ((sizeof(KeyT) == 8 && HAS_VAL) ? 1 : 4)); }
 
 // ---------------------------------------------------------------------------------------------
 // Generic multi-block exclusive scan (u64), chunk = 4096 elements per CTA
