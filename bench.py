@@ -53,7 +53,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", delete=False, suffix=".csv")
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 

@@ -355,12 +355,18 @@ VB_D u32 table_find(const Table &t, u64 key)
 // ---------------------------------------------------------------------------------------------
 // Radix pass (stable multisplit / one LSD digit)
 // ---------------------------------------------------------------------------------------------
+#ifndef VB_RP_TILE
+#define VB_RP_TILE 4096
+#endif
+#ifndef VB_RPS_THREADS
+#define VB_RPS_THREADS 512
+#endif
 constexpr int RP_THREADS = 256;
 constexpr int RP_WARPS = RP_THREADS / 32;
-constexpr int RP_ITEMS = 16;
-constexpr int RP_TILE = RP_THREADS * RP_ITEMS;   // 4096 rows
+constexpr int RP_TILE = VB_RP_TILE;              // rows per tile
+constexpr int RP_ITEMS = RP_TILE / RP_THREADS;   // histogram kernel: items per thread per tile
 constexpr int RP_NB = 256;                       // bins of an 8-bit pass (multisplit); bin NB = "invalid, drop"
-constexpr int RPS_THREADS = 512;                 // scatter kernel: 16 warps x 8 items cover the same 4096-row tile with
+constexpr int RPS_THREADS = VB_RPS_THREADS;      // scatter kernel: 16 warps x 8 items cover the same 4096-row tile with
 constexpr int RPS_WARPS = RPS_THREADS / 32;      // <= 64 registers/thread, so 2 CTAs = 32 warps stay resident per SM
 constexpr int RPS_ITEMS = RP_TILE / RPS_THREADS; // (256 x 16 needed 128 registers: 16 warps/SM, issue slots 32 % busy)
 constexpr int RP_SORT_BITS = 8;                  // digit width of the LSD sort passes; a 10-bit variant was measured 2.4x slower per pass
@@ -471,7 +477,7 @@ VB_D u32 warp_match_digit(u32 d)
 // math_pipe_throttle in profiles/r1_ncu_rp_ballot.txt) every LANE keeps private byte counters
 // pc[warp][digit][lane] in shared memory: an item is one LDS.U8 / IADD / STS.U8, no atomics, no votes.
 // A thread adds at most RP_ITEMS per tile, so the bytes are folded into the CTA's u32 histogram
-// every 15 tiles (15 * 16 = 240 <= 255).
+// every 255 / RP_ITEMS tiles (15 * 16 = 240 <= 255).
 constexpr size_t rp_hist_smem(int bits) { return (size_t)RP_WARPS * ((size_t)1 << bits) * 32; }
 
 template <typename KeyT, int LDM, int DGM, int BITS>
@@ -526,7 +532,7 @@ rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ 
                 }
             }
         }
-        if (++tiles_since_fold == 15) { fold(); tiles_since_fold = 0; }
+        if (++tiles_since_fold == 255 / RP_ITEMS) { fold(); tiles_since_fold = 0; }
     }
     fold();
     __syncthreads();
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(1024) rp_scan_kernel(u32 *hist, u32 len)
 // rows (runs of ~16 rows per digit → coalesced 64-128 B segments).  5 barriers per tile; the counters
 // for the next tile are cleared and its loads are in flight while the current tile is written out.
 template <typename KeyT, bool HAS_VAL, int LDM, int DGM, int BITS>
-__global__ void __launch_bounds__(RPS_THREADS, 2)
+__global__ void __launch_bounds__(RPS_THREADS, (RPS_THREADS > 512 ? 1 : 2))
 rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
                   KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals)
 {
