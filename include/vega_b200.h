@@ -138,10 +138,30 @@ VB_API int32_t vb_shuffle_map_soa(vb_shuf *s, uint32_t map_id, const void *keys,
  * rank (combined rows for reduce ops, raw rows in map order for group ops); counts[world] gets
  * rows per destination.  export_buffers returns the packed device arrays (destination-major).
  * The host exchanges them (one all-to-all-v over NCCL) and hands the received rows, source-rank
- * major, to vb_shuffle_import.  Then vb_shuffle_seal.                                        */
+ * major, to vb_shuffle_import (the buffers are borrowed until vb_shuffle_seal returns).  Then vb_shuffle_seal. */
 VB_API int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts);
 VB_API int32_t vb_shuffle_export_buffers(vb_shuf *s, void **keys_dev, void **vals_dev);
 VB_API int32_t vb_shuffle_import(vb_shuf *s, const void *keys_dev, const void *vals_dev, const uint64_t *counts);
+
+/* Fused exchange for GROUP/COGROUP shuffles (world > 1, one process per GPU on one NVLink/NVSwitch node):
+ * the destination-rank partition kernel stores every row straight into the HBM of the rank that owns its
+ * reduce partition (peer memory mapped with CUDA IPC), so there is no pack buffer and no separate
+ * collective — the transfer overlaps the partitioning tile by tile.  Protocol (vega_b200/dist.py drives it):
+ *   1. vb_shuffle_export_counts(s, counts[world])        rows this rank sends to each rank (histogram only)
+ *   2. ranks all-gather the counts; each reserves its receive arena for sum_src counts[src][me] rows
+ *      (16 B/row: keys[total] then vals[total]) with vb_ctx_arena_reserve -> 64-byte IPC handle + generation
+ *   3. ranks all-gather the handles; vb_ctx_peer_open(ctx, peer, handle, generation, is_self) maps them (cached
+ *      per generation; is_self != 0 for the caller's own rank)
+ *   4. vb_shuffle_export_direct(s, dst_row_offset[world], dst_total_rows[world]) runs the scatter; it returns when
+ *      this rank's stores are complete; the host then barriers all ranks
+ *   5. vb_shuffle_import_arena(s, counts_from_each_src[world]); vb_shuffle_seal(s)
+ * The arena is reused (and only grows) across shuffles of the context; a shuffle must be sealed before the
+ * next one's export_direct targets the same arena.                                                            */
+VB_API int32_t vb_ctx_arena_reserve(vb_ctx *ctx, uint64_t bytes, void *handle_out /*64 bytes*/, uint64_t *generation);
+VB_API int32_t vb_ctx_peer_open(vb_ctx *ctx, uint32_t peer_rank, const void *handle /*64 bytes*/, uint64_t generation, int32_t is_self);
+VB_API int32_t vb_shuffle_export_counts(vb_shuf *s, uint64_t *counts);
+VB_API int32_t vb_shuffle_export_direct(vb_shuf *s, const uint64_t *dst_row_offset, const uint64_t *dst_total_rows);
+VB_API int32_t vb_shuffle_import_arena(vb_shuf *s, const uint64_t *counts);
 
 /* All map outputs are registered: run the reduce side for every partition this rank owns.
  * world == 1: every map_id in [0, n_map) must have been submitted.                          */

@@ -34,7 +34,7 @@ def _dataset():
     return keys, vals
 
 
-def _worker(rank, world, port, agg, M, R, nccl, outdir):
+def _worker(rank, world, port, agg, M, R, nccl, outdir, p2p=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -53,7 +53,13 @@ def _worker(rank, world, port, agg, M, R, nccl, outdir):
     eng = vdist.CudaEngine(sc)
     maps = [(m, keys[starts[m]:starts[m + 1]], vals[starts[m]:starts[m + 1]]) for m in range(lo, hi)]
     stats = {}
-    sh = vdist.run_shuffle(eng, maps, M, R, 0, 0, agg, rank, world, stats=stats, exchange_device=None if nccl else "cpu")
+    sh = vdist.run_shuffle(eng, maps, M, R, 0, 0, agg, rank, world, stats=stats, exchange_device=None if nccl else "cpu", p2p=p2p)
+    if p2p and agg == 0:
+        assert stats.get("exchange_kind") == "p2p"
+        # a second shuffle through the same (cached) arena and peer mappings
+        sh.free()
+        stats = {}
+        sh = vdist.run_shuffle(eng, maps, M, R, 0, 0, agg, rank, world, stats=stats, p2p=True)
     res = {}
     for r in range(R):
         out = sh.reduce(r)
@@ -67,13 +73,16 @@ def _worker(rank, world, port, agg, M, R, nccl, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("agg,M,R", [(1, 4, 4), (0, 4, 6), (4, 6, 3), (2, 2, 8), (0, 5, 2)])
-def test_two_rank_cuda_shuffle_matches_oracle(agg, M, R):
+@pytest.mark.parametrize("agg,M,R,p2p", [(1, 4, 4, False), (0, 4, 6, False), (4, 6, 3, False), (2, 2, 8, False), (0, 5, 2, False),
+                                         (0, 4, 6, True), (0, 3, 2, True)])
+def test_two_rank_cuda_shuffle_matches_oracle(agg, M, R, p2p):
+    """p2p=True: the fused exchange — rows are stored by the partition kernel directly into the other rank's
+    arena through a CUDA IPC mapping (same GPU on a 1-GPU box, NVLink peer on a multi-GPU box)."""
     from oracle import oracle as O
     world = 2
     nccl = torch.cuda.device_count() >= 2
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), agg, M, R, nccl, d), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), agg, M, R, nccl, d, p2p), nprocs=world, join=True)
         per_rank = [pickle.load(open(os.path.join(d, f"r{r}.pkl"), "rb")) for r in range(world)]
     keys, vals = _dataset()
     op = {0: "group", 1: "sum", 2: "min", 3: "max", 4: "count"}[agg]

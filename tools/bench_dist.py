@@ -27,6 +27,7 @@ ap.add_argument("--rows", type=float, default=1e9, help="rows per GPU")
 ap.add_argument("--distinct", type=float, default=1e6)
 ap.add_argument("--ops", default="zipf,join,group")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--p2p", action="store_true", help="fused partition+send over peer memory for group/join")
 args = ap.parse_args()
 rank, world, lrank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lrank)
@@ -66,7 +67,7 @@ def shuffle(rows, maps_per_rank, R, agg, stats):
     starts = vb.slice_starts(rows.shape[0], maps_per_rank)
     lo, _ = vdist.map_block(rank, world, maps_per_rank * world)
     maps = [(lo + m, rows[int(starts[m]):int(starts[m + 1])], None) for m in range(maps_per_rank)]
-    return vdist.run_shuffle(eng, maps, maps_per_rank * world, R, L.VB_U64, L.VB_U64, agg, rank, world, stats=stats)
+    return vdist.run_shuffle(eng, maps, maps_per_rank * world, R, L.VB_U64, L.VB_U64, agg, rank, world, stats=stats, p2p=args.p2p)
 
 
 def timed(fn):
@@ -133,7 +134,7 @@ if "group" in ops:
     dt, (nk, nv, st) = timed(run)
     sent = 16 * st.get("sent_rows", 0)
     xms = st.get("exchange_ms") or 0.0
-    emit({"op": "group_by_key uniform", "n_gpus": world, "rows_total": n * world, "partitions": R, "s": dt, "rows_per_s": n * world / dt,
+    emit({"op": "group_by_key uniform" + (" [p2p fused exchange]" if args.p2p else " [NCCL all-to-all-v]"), "n_gpus": world, "rows_total": n * world, "partitions": R, "s": dt, "rows_per_s": n * world / dt,
           "groups_out": int(allsum(float(nk))), "values_out": int(allsum(float(nv))), "values_match_input": int(allsum(float(nv))) == n * world,
           "exchange_ms": xms, "bytes_sent_per_rank": sent,
           "nvlink_all_to_all_GBps_per_rank": (sent / (xms * 1e-3) / 1e9) if xms else None})
@@ -167,7 +168,7 @@ if "join" in ops:
     dt, (tot, st) = timed(run)
     out_rows = int(allsum(float(tot)))
     sent = 16 * st.get("sent_rows", 0)
-    emit({"op": "join unique keys [configs[3]]", "n_gpus": world, "rows_per_side_total": n * world, "partitions": R, "s": dt,
+    emit({"op": "join unique keys [configs[3]]" + (" [p2p]" if args.p2p else " [NCCL]"), "n_gpus": world, "rows_per_side_total": n * world, "partitions": R, "s": dt,
           "input_rows_per_s": 2 * n * world / dt, "join_rows": out_rows, "join_rows_expected": shared_total,
           "exchange_ms_both_sides": st.get("exchange_ms"), "bytes_sent_per_rank_last_side": sent})
 sc.close()

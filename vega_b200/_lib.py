@@ -56,6 +56,11 @@ SYMBOLS = {
     "vb_shuffle_export_prepare": (_i32, [_vp, _pu64]),
     "vb_shuffle_export_buffers": (_i32, [_vp, _pvp, _pvp]),
     "vb_shuffle_import": (_i32, [_vp, _vp, _vp, _pu64]),
+    "vb_ctx_arena_reserve": (_i32, [_vp, _u64, _vp, _pu64]),
+    "vb_ctx_peer_open": (_i32, [_vp, _u32, _vp, _u64, _i32]),
+    "vb_shuffle_export_counts": (_i32, [_vp, _pu64]),
+    "vb_shuffle_export_direct": (_i32, [_vp, _pu64, _pu64]),
+    "vb_shuffle_import_arena": (_i32, [_vp, _pu64]),
     "vb_shuffle_seal": (_i32, [_vp]),
     "vb_shuffle_is_sealed": (_i32, [_vp]),
     "vb_shuffle_reduce_size": (_i32, [_vp, _u32, _pu64, _pu64]),

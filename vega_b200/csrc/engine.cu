@@ -70,6 +70,12 @@ struct vb_ctx {
     u64 zipf_n = 0;
     double zipf_s = 0;
     std::map<const void *, int> occ_cache;
+    // P2P exchange: this rank's receive arena (cudaMalloc'ed, exported with CUDA IPC) and the peers' arenas
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    u64 arena_gen = 0;
+    struct Peer { void *base = nullptr; u64 gen = 0; bool self = false; };
+    std::map<u32, Peer> peers;
 };
 
 struct DevBuf {   // stream-ordered device allocation, freed on scope exit unless released
@@ -154,6 +160,8 @@ extern "C" int32_t vb_ctx_destroy(vb_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->zipf_cdf) cudaFreeAsync(c->zipf_cdf, c->stream);
     cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->peers) if (kv.second.base && !kv.second.self) cudaIpcCloseMemHandle(kv.second.base);
+    if (c->arena) cudaFree(c->arena);
     cudaFreeHost(c->h_scratch);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -235,6 +243,13 @@ struct vb_shuf {
     // export / import (world > 1)
     bool exported = false, imported = false;
     u64 *exp_keys = nullptr, *exp_vals = nullptr;
+    // fused export (P2P): plan + scanned histogram + gathered input kept between export_counts and export_direct
+    u32 *exp_hist = nullptr;
+    u32 exp_parts = 0;
+    u64 exp_rows_per_part = 0, exp_n = 0;
+    const u64 *exp_rows = nullptr, *exp_k = nullptr, *exp_v = nullptr;
+    std::vector<u64> exp_digit_start;
+    bool exp_counted = false;
     const u64 *imp_keys = nullptr, *imp_vals = nullptr;
     u64 imp_n = 0;
     // gathered input kept alive for the reduce side of group ops
@@ -625,18 +640,14 @@ static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
 // One stable pass: rows of `ld` (n of them) are written to out_keys/out_vals grouped by digit.
 // d_hist (device, plan.hist_bytes()) afterwards holds the scanned histogram: d_hist[d*num_parts]
 // is the output offset of digit d, d_hist[nb*num_parts] the number of valid rows.
-template <typename KeyT, bool HAS_VAL>
-static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist,
-                      const PassPlan &plan)
+template <typename KeyT>
+static int radix_hist_scan(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, u32 *d_hist, const PassPlan &plan)
 {
     vb_ctx *c = s->ctx;
     if (n == 0 || plan.num_parts == 0) return VB_OK;
     const int bits = plan.nb == 256 ? 8 : RP_SORT_BITS;
     const void *hk = hist_fn<KeyT>(ld.mode, dg.mode, bits);
-    const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode, bits);
-    if (!hk || !sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d / %d bits not instantiated", ld.mode, dg.mode, bits);
-    const size_t smem = scatter_smem<KeyT, HAS_VAL>(bits);
-    CU(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!hk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d / %d bits not instantiated", ld.mode, dg.mode, bits);
     const u64 tiles_per_part = plan.rows_per_part / RP_TILE;
     u32 split = (u32)std::max<u64>(1, std::min<u64>(tiles_per_part, ((u64)c->sm_count * 6 + plan.num_parts - 1) / plan.num_parts));
     CU(cudaMemsetAsync(d_hist, 0, plan.hist_bytes(), c->stream));
@@ -657,10 +668,30 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
         rp_scan_kernel<<<1, 1024, 0, c->stream>>>(d_hist, plan.nb * plan.num_parts);
         TRY(kl.done("rp_scan_kernel"));
     }
+    return VB_OK;
+}
+
+template <typename KeyT, bool HAS_VAL>
+static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist,
+                      const PassPlan &plan)
+{
+    vb_ctx *c = s->ctx;
+    if (n == 0 || plan.num_parts == 0) return VB_OK;
+    const int bits = plan.nb == 256 ? 8 : RP_SORT_BITS;
+    const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode, bits);
+    if (!sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d / %d bits not instantiated", ld.mode, dg.mode, bits);
+    TRY((radix_hist_scan<KeyT>(s, ld, dg, n, d_hist, plan)));
+    const size_t smem = scatter_smem<KeyT, HAS_VAL>(bits);
+    CU(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    u64 rows_per_part = plan.rows_per_part;
+    u32 num_parts = plan.num_parts;
+    Loader ldc = ld;
+    Digit dgc = dg;
     {
         KLaunch kl(s, K_RP_SCATTER, n);
         const u32 *ch = d_hist;
-        void *args[] = {&ldc, &dgc, &n, &rows_per_part, &ch, &num_parts, &out_keys, &out_vals};
+        RemoteDst rd{nullptr, nullptr, nullptr, 0};
+        void *args[] = {&ldc, &dgc, &n, &rows_per_part, &ch, &num_parts, &out_keys, &out_vals, &rd};
         CU(cudaLaunchKernel(sk, dim3(plan.num_parts), dim3(RPS_THREADS), args, smem, c->stream));
         TRY(kl.done("rp_scatter_kernel"));
     }
@@ -1174,7 +1205,9 @@ static void release_inputs(vb_shuf *s)
     s->gath_keys = s->gath_vals = nullptr;
     dev_free(s->ctx, s->exp_keys);
     dev_free(s->ctx, s->exp_vals);
+    dev_free(s->ctx, s->exp_hist);
     s->exp_keys = s->exp_vals = nullptr;
+    s->exp_hist = nullptr;
 }
 
 extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
@@ -1222,6 +1255,161 @@ extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
     CU(cudaStreamSynchronize(c->stream));
     std::lock_guard<std::mutex> g(s->mu);
     s->exported = true;
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// P2P exchange: rows go straight from the partition kernel into the peers' HBM over NVLink
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t vb_ctx_arena_reserve(vb_ctx *c, uint64_t bytes, void *handle_out, uint64_t *generation)
+{
+    if (!c || !handle_out || !generation) return set_err(VB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (bytes > c->arena_bytes || !c->arena) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->arena) CU(cudaFree(c->arena));
+        c->arena = nullptr;
+        size_t want = std::max<size_t>((size_t)bytes + bytes / 4, (size_t)64 << 20);
+        want = (want + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        CU(cudaMalloc(&c->arena, want));     // cudaMalloc, not the async pool: legacy IPC handles need it
+        c->arena_bytes = want;
+        c->arena_gen++;
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->arena));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, sizeof(h));
+    *generation = c->arena_gen;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_peer_open(vb_ctx *c, uint32_t peer_rank, const void *handle, uint64_t generation, int32_t is_self)
+{
+    if (!c || (!handle && !is_self)) return set_err(VB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    auto &p = c->peers[peer_rank];
+    if (is_self) { p.base = c->arena; p.gen = c->arena_gen; p.self = true; return VB_OK; }
+    if (p.base && p.gen == generation && !p.self) return VB_OK;
+    if (p.base && !p.self) { CU(cudaStreamSynchronize(c->stream)); cudaIpcCloseMemHandle(p.base); p.base = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    p.base = base; p.gen = generation; p.self = false;
+    return VB_OK;
+}
+
+// Histogram of this rank's rows by destination rank (no data movement yet); keeps the scanned
+// per-part histogram for vb_shuffle_export_direct.  group ops only (reduce ops exchange a few MB of
+// combined rows: vb_shuffle_export_prepare + one all-to-all-v is the right tool there).
+extern "C" int32_t vb_shuffle_export_counts(vb_shuf *s, uint64_t *counts)
+{
+    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_export_counts needs vb_shuffle_set_dist(world > 1)");
+    if (!is_group_op(s->agg)) return set_err(VB_ERR_UNSUPPORTED, "the fused P2P export is for GROUP/COGROUP shuffles");
+    vb_ctx *c = s->ctx;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->sealed || s->exported || s->exp_counted || s->freed) return set_err(VB_ERR_STATE, "export after seal/export");
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    Gathered g;
+    TRY(gather_maps(s, &g));
+    s->exp_rows = g.rows; s->exp_k = g.keys; s->exp_v = g.vals; s->exp_n = g.n;
+    s->exp_digit_start.assign((size_t)s->world + 1, 0);
+    if (g.n) {
+        PassPlan plan = plan_pass<u64, true>(c, g.n, 8);
+        DevBuf hist(c);
+        TRY(hist.alloc(plan.hist_bytes()));
+        Loader ld = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
+        Digit dg = make_bucket_digit(s, DG_DEST, 0, 0xFFFFFFFFu);
+        TRY((radix_hist_scan<u64>(s, ld, dg, g.n, hist.as<u32>(), plan)));
+        TRY(fetch_offsets(c, hist.as<u32>(), plan, s->world, s->exp_digit_start.data()));
+        s->exp_hist = (u32 *)hist.release();
+        s->exp_parts = plan.num_parts;
+        s->exp_rows_per_part = plan.rows_per_part;
+    }
+    for (u32 r = 0; r < s->world; ++r) counts[r] = s->exp_digit_start[r + 1] - s->exp_digit_start[r];
+    std::lock_guard<std::mutex> gg(s->mu);
+    s->exp_counted = true;
+    return VB_OK;
+}
+
+// The scatter: every row is stored into the arena of the rank that owns its reduce partition.
+// dst_row_offset[d]: first row of my block inside rank d's arena; dst_total_rows[d]: rows rank d receives in total
+// (its arena holds keys[total] then vals[total]).  Returns after the stores are complete on this GPU; the
+// host then barriers the ranks before anyone reads its arena.
+extern "C" int32_t vb_shuffle_export_direct(vb_shuf *s, const uint64_t *dst_row_offset, const uint64_t *dst_total_rows)
+{
+    if (!s || !dst_row_offset || !dst_total_rows) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (!s->exp_counted || s->exported) return set_err(VB_ERR_STATE, "vb_shuffle_export_direct needs vb_shuffle_export_counts first");
+    vb_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const u32 W = s->world;
+    if (s->exp_n) {
+        std::vector<u64 *> hk(W), hv(W);
+        std::vector<u32> hadj(W);
+        for (u32 d = 0; d < W; ++d) {
+            auto it = c->peers.find(d);
+            const u64 cnt = s->exp_digit_start[d + 1] - s->exp_digit_start[d];
+            if (it == c->peers.end() || !it->second.base) {
+                if (cnt) return set_err(VB_ERR_STATE, "peer %u arena not opened (vb_ctx_peer_open)", d);
+                hk[d] = hv[d] = nullptr; hadj[d] = 0;
+                continue;
+            }
+            if (dst_row_offset[d] + cnt > dst_total_rows[d] || dst_total_rows[d] >= 0xFFFFFFFFull)
+                return set_err(VB_ERR_INVALID, "bad arena layout for destination %u", d);
+            hk[d] = (u64 *)it->second.base;
+            hv[d] = hk[d] + dst_total_rows[d];
+            hadj[d] = (u32)(dst_row_offset[d] - s->exp_digit_start[d]);
+        }
+        DevBuf dk(c), dv(c), da(c);
+        TRY(dk.alloc(W * 8)); TRY(dv.alloc(W * 8)); TRY(da.alloc(W * 4));
+        CU(cudaMemcpyAsync(dk.p, hk.data(), W * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(dv.p, hv.data(), W * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(da.p, hadj.data(), W * 4, cudaMemcpyHostToDevice, c->stream));
+        Loader ld = s->exp_rows ? Loader{LD_AOS64, s->exp_rows, nullptr, 0} : Loader{LD_SOA64, s->exp_k, s->exp_v, 0};
+        Digit dg = make_bucket_digit(s, DG_DEST, 0, 0xFFFFFFFFu);
+        const void *sk = s->exp_rows ? (const void *)rp_scatter_kernel<u64, true, LD_AOS64, DG_DEST, 8, true>
+                                     : (const void *)rp_scatter_kernel<u64, true, LD_SOA64, DG_DEST, 8, true>;
+        const size_t smem = scatter_smem<u64, true>(8);
+        CU(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        u64 n = s->exp_n, rpp = s->exp_rows_per_part;
+        u32 np = s->exp_parts;
+        const u32 *ch = s->exp_hist;
+        u64 *nullk = nullptr, *nullv = nullptr;
+        RemoteDst rd{dk.as<u64 *>(), dv.as<u64 *>(), da.as<u32>(), W};
+        KLaunch kl(s, K_RP_SCATTER, n);
+        void *args[] = {&ld, &dg, &n, &rpp, &ch, &np, &nullk, &nullv, &rd};
+        CU(cudaLaunchKernel(sk, dim3(np), dim3(RPS_THREADS), args, smem, c->stream));
+        TRY(kl.done("rp_scatter_kernel<REMOTE>"));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    dev_free(c, s->exp_hist);
+    s->exp_hist = nullptr;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->exported = true;
+    return VB_OK;
+}
+
+// The rows of every source rank are already in this context's arena (keys[total] then vals[total],
+// source-rank major): hand them to the reduce side.  counts[world] as in vb_shuffle_import.
+extern "C" int32_t vb_shuffle_import_arena(vb_shuf *s, const uint64_t *counts)
+{
+    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (!s->exported || s->sealed) return set_err(VB_ERR_STATE, "import needs the export first and no seal yet");
+    u64 n = 0;
+    for (u32 r = 0; r < s->world; ++r) n += counts[r];
+    if (n * 16 > s->ctx->arena_bytes) return set_err(VB_ERR_INVALID, "arena holds %zu bytes, %llu rows announced", s->ctx->arena_bytes, (unsigned long long)n);
+    if (n >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "import of %llu rows", (unsigned long long)n);
+    s->imp_keys = (const u64 *)s->ctx->arena;
+    s->imp_vals = s->imp_keys + n;
+    s->imp_n = n;
+    s->imported = true;
     return VB_OK;
 }
 

@@ -586,10 +586,23 @@ __global__ void __launch_bounds__(1024) rp_scan_kernel(u32 *hist, u32 len)
 // row's GLOBAL output index, then write it out with consecutive threads touching consecutive staged
 // rows (runs of ~16 rows per digit → coalesced 64-128 B segments).  5 barriers per tile; the counters
 // for the next tile are cleared and its loads are in flight while the current tile is written out.
-template <typename KeyT, bool HAS_VAL, int LDM, int DGM, int BITS>
+// Destination tables of a REMOTE scatter: digit d (= destination rank) is written to the peer's
+// receive arena mapped into this process (CUDA IPC over NVLink), at row adj[d] + flat_index.
+struct RemoteDst {
+    u64 *const *keys;   // [world] device array of peer key bases
+    u64 *const *vals;   // [world]
+    const u32 *adj;     // [world] (my row offset inside the peer's arena) - (start of digit d in the flat order)
+    u32 world;
+};
+
+// REMOTE = the shuffle's exchange fused into the partition pass: instead of packing rows by
+// destination rank locally and handing the buffers to an all-to-all, the staged runs are stored straight
+// into the destination GPUs' HBM (st.global on peer-mapped addresses), so the NVLink transfer overlaps
+// ranking/staging of the following tiles.
+template <typename KeyT, bool HAS_VAL, int LDM, int DGM, int BITS, bool REMOTE = false>
 __global__ void __launch_bounds__(RPS_THREADS, (RPS_THREADS > 512 ? 1 : 2))
 rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
-                  KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals)
+                  KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals, RemoteDst rd)
 {
     constexpr int NB = 1 << BITS;
     static_assert(NB + 1 <= RPS_THREADS, "one thread per digit in the tile scan");
@@ -606,6 +619,12 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
     __shared__ u32 gbase[NB + 1];            // run_off[d] - dbase[d]: staged position p of digit d goes to gbase[d] + p
     __shared__ u32 run_off[NB];              // global output offset of the next row of digit d for this part
     __shared__ u32 wtot[RPS_WARPS];
+    __shared__ u64 *s_dk[REMOTE ? NB : 1];
+    __shared__ u64 *s_dv[REMOTE ? NB : 1];
+    __shared__ u32 s_adj[REMOTE ? NB : 1];
+    static_assert(!REMOTE || (sizeof(KeyT) == 8 && HAS_VAL), "remote scatter moves (u64 key, u64 value) rows");
+    if (REMOTE)
+        for (u32 d = threadIdx.x; d < rd.world && d < (u32)NB; d += RPS_THREADS) { s_dk[d] = rd.keys[d]; s_dv[d] = rd.vals[d]; s_adj[d] = rd.adj[d]; }
 
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const u32 lt = lanemask_lt();
@@ -689,9 +708,16 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
         for (u32 d = tid; d < RPS_WARPS * (NB + 1); d += RPS_THREADS) (&cnt[0][0])[d] = 0;
         const u32 n_valid = dbase[NB];
         for (u32 p = tid; p < n_valid; p += RPS_THREADS) {
-            const u32 o = STAGE_IDX ? stage_out[p] : gbase[stage_dig[p]] + p;
-            out_keys[o] = stage_keys[p];
-            if (HAS_VAL) out_vals[o] = stage_vals[p];
+            if (REMOTE) {
+                const u32 d = stage_dig[p];
+                const u32 o = gbase[d] + p + s_adj[d];
+                s_dk[d][o] = (u64)stage_keys[p];
+                s_dv[d][o] = stage_vals[p];
+            } else {
+                const u32 o = STAGE_IDX ? stage_out[p] : gbase[stage_dig[p]] + p;
+                out_keys[o] = stage_keys[p];
+                if (HAS_VAL) out_vals[o] = stage_vals[p];
+            }
         }
         __syncthreads();                                                        // B5: staging buffers and cnt reusable
     }

@@ -79,6 +79,48 @@ class CudaEngine:
         return sh.reduce(r)
 
 
+def p2p_exchange(engine, sh, rank, world, group=None, stats=None):
+    """Fused exchange of a GROUP/COGROUP shuffle: the partition kernel of every rank stores its rows straight
+    into the owners' HBM (CUDA IPC peer mappings over NVLink) — see include/vega_b200.h.  torch.distributed only
+    carries the control plane: two small all-gathers (counts, IPC handles) and one barrier."""
+    import torch
+    import torch.distributed as dist
+    lib, sc = sh._lib, engine.sc
+    t0 = None
+    if stats is not None:
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+    counts = (ctypes.c_uint64 * world)()
+    L.check(lib.vb_shuffle_export_counts(sh._h, counts))
+    counts = [int(c) for c in counts]
+    allc = [None] * world
+    dist.all_gather_object(allc, counts, group=group)            # allc[src][dst]
+    total_recv = [sum(allc[src][dst] for src in range(world)) for dst in range(world)]
+    my_off = [sum(allc[src][dst] for src in range(rank)) for dst in range(world)]
+    handle = (ctypes.c_ubyte * 64)()
+    gen = ctypes.c_uint64()
+    L.check(lib.vb_ctx_arena_reserve(sc._h, 16 * max(total_recv[rank], 1), handle, ctypes.byref(gen)))
+    allh = [None] * world
+    dist.all_gather_object(allh, (bytes(handle), gen.value), group=group)   # doubles as "every arena is reserved"
+    for peer, (hb, g) in enumerate(allh):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(hb)
+        L.check(lib.vb_ctx_peer_open(sc._h, peer, buf, g, int(peer == rank)))
+    off = (ctypes.c_uint64 * world)(*my_off)
+    tot = (ctypes.c_uint64 * world)(*total_recv)
+    L.check(lib.vb_shuffle_export_direct(sh._h, off, tot))        # returns when this rank's stores are done
+    dist.barrier(group=group)                                     # everybody's rows have landed
+    rc = (ctypes.c_uint64 * world)(*[allc[src][rank] for src in range(world)])
+    L.check(lib.vb_shuffle_import_arena(sh._h, rc))
+    if stats is not None:
+        torch.cuda.synchronize()
+        stats["exchange_ms"] = stats.get("exchange_ms", 0.0) + (time.perf_counter() - t0) * 1e3
+        stats["sent_rows"] = sum(counts) - counts[rank]
+        stats["recv_rows"] = total_recv[rank] - allc[rank][rank]
+        stats["exchanges"] = stats.get("exchanges", 0) + 1
+        stats["exchange_kind"] = "p2p"
+
+
 def all_to_all_v(send_keys, send_vals, send_counts, group=None):
     """The shuffle's single exchange step: counts, then keys and values, each one
     all_to_all_single.  Returns (recv_keys, recv_vals, recv_counts), source-rank major."""
@@ -97,17 +139,20 @@ def all_to_all_v(send_keys, send_vals, send_counts, group=None):
 
 
 def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, world, group=None, key_width=8, hint=0,
-                stats=None, exchange_device=None):
+                stats=None, exchange_device=None, p2p=False):
     """Map side on this rank's partitions → exchange → reduce side for the partitions this rank owns.
 
     local_maps: [(map_id, keys, vals_or_None)], ascending map ids from map_block(rank, world, n_map).
     Returns the sealed engine handle; engine.reduce(h, r) is non-empty only for r % world == rank.
     exchange_device: move the packed buffers there for the collective (tests: "cpu" + gloo on a 1-GPU box).
+    p2p: GROUP/COGROUP shuffles use the fused partition+send over peer memory instead of pack + all-to-all-v.
     """
     sh = engine.create(n_map, n_reduce, kcode, vcode, agg, rank, world, key_width=key_width, hint=hint)
     for map_id, keys, vals in local_maps:
         engine.map(sh, map_id, keys, vals)
-    if world > 1:
+    if world > 1 and p2p and agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP) and isinstance(engine, CudaEngine):
+        p2p_exchange(engine, sh, rank, world, group, stats)
+    elif world > 1:
         counts, sk, sv = engine.export(sh, world)
         home = sk.device
         if exchange_device is not None:        # e.g. "cpu" for a gloo group: stage the exchange through the host
