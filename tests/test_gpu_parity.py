@@ -461,3 +461,43 @@ def test_bincode_blobs_encode_decode(sc):
             bad.map_blob(0, blob)
         assert e.value.code == -1
     bad.free()
+
+
+def test_shared_table_of_borrowed_map_tasks(sc):
+    """Map tasks with VB_DEVICE_BORROWED input combine into one shared table, launched without a host round
+    trip; overflow and map-id resubmission are repaired at seal from the still-borrowed inputs."""
+    import torch
+    rng = np.random.default_rng(123)
+    keys, vals = rand_pairs(rng, 400_000, 150_000)
+    tk = torch.from_numpy(keys.view(np.int64)).cuda()
+    tv = torch.from_numpy(vals.view(np.int64)).cuda()
+    want = oracle_reduce("sum", keys, vals, 4, 3)
+    # (a) plain
+    got = gpu_reduce_parts(sc.parallelize((tk, tv), 4).reduce_by_key("sum", 3))
+    assert [{k & (2 ** 64 - 1): v & (2 ** 64 - 1) for k, v in d.items()} for d in got] == want
+    # (b) a wrong hint (100 keys) makes the shared table overflow: seal must rebuild it larger
+    rdd = sc.parallelize((tk, tv), 4).reduce_by_key("sum", 3, hint=100)
+    got = gpu_reduce_parts(rdd)
+    assert [{k & (2 ** 64 - 1): v & (2 ** 64 - 1) for k, v in d.items()} for d in got] == want
+    assert rdd.stats()["table_restarts"] >= 1
+    # (c) resubmitting a map id must not double count; mixing borrowed and host-copied map tasks merges both
+    starts = vb.slice_starts(len(keys), 4)
+    sh = vb.Shuffle(sc, 4, 3, 0, 1, 1)
+    ck, cv = vb.rdd._Col(tk), vb.rdd._Col(tv)
+    hk, hv = vb.rdd._Col(keys), vb.rdd._Col(vals)
+    for m in range(4):
+        if m == 2:
+            sh.map(m, hk, hv, int(starts[m]), int(starts[m + 1]))       # host input: per-map table
+        else:
+            sh.map(m, ck, cv, int(starts[m]), int(starts[m + 1]))
+    sh.map(1, ck, cv, int(starts[1]), int(starts[2]))                   # resubmission of a borrowed task
+    sh.seal()
+    for r in range(3):
+        k, c = sh.reduce(r)
+        assert {int(a) & (2 ** 64 - 1): int(b) & (2 ** 64 - 1) for a, b in zip(k, c)} == want[r]
+    sh.free()
+    # (d) min over f64 through the shared table (order-preserving transform + hot-key cache flush)
+    fv = torch.from_numpy(rng.standard_normal(len(keys))).cuda()
+    gotf = gpu_reduce_parts(sc.parallelize((tk, fv), 4).reduce_by_key("min", 3))
+    wantf = oracle_reduce("min", keys, fv.cpu().numpy(), 4, 3, "f64")
+    assert [{k & (2 ** 64 - 1): v for k, v in d.items()} for d in gotf] == wantf

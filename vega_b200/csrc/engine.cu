@@ -212,6 +212,7 @@ struct MapOut {
     const u64 *keys = nullptr;
     const u64 *vals = nullptr;
     bool owned = false;
+    bool in_shared = false;   // reduce ops, borrowed device input: combined straight into the shuffle's shared table
 };
 
 struct Timer {
@@ -235,6 +236,15 @@ struct vb_shuf {
     u32 key_width = 8;
     u64 hint = 0;
     u64 learned_distinct = 0;      // distinct keys seen by the previous table build of this shuffle
+    // Shared table of the map tasks whose input is VB_DEVICE_BORROWED (valid until seal): the named ops are
+    // associative and commutative, so those tasks combine into ONE table, launched back to back without a
+    // host round trip per task and without a merge at seal.  If it overflows, or a map id is resubmitted,
+    // seal rebuilds it from the still-borrowed inputs (same restart logic as build_table).
+    void *sh_tab = nullptr;
+    u32 sh_log_cap = 0;
+    TableCtl *sh_ctl = nullptr;
+    u64 sh_max_inserts = 0;
+    bool sh_dirty = false;
     u32 rank = 0, world = 1;
     std::vector<MapOut> maps;
     std::mutex mu;
@@ -476,6 +486,18 @@ static int estimate_distinct(vb_shuf *s, const std::vector<AggInput> &inputs, u6
     return VB_OK;
 }
 
+// First table size.  Load factor <= 0.4 while the table (16 B/slot) still fits comfortably in L2 (<= 64 MB),
+// where a fuller 4-key bucket costs a second dependent probe (2.9 vs 2.2 ms per 2.5e8 rows at load 0.48 vs
+// 0.24, profiles/r1_micro_v4_bucketized.log); <= 0.5 for bigger tables, which pay DRAM traffic instead.
+static u32 choose_log_cap(u64 total, u64 hint_distinct, bool estimated, u32 max_log)
+{
+    u64 target = hint_distinct ? (hint_distinct * 5) / 2 : std::min<u64>(2 * std::max<u64>(total, 1), 1ull << 21);
+    if (hint_distinct && target > (1ull << 22)) target = 2 * hint_distinct;
+    // an estimate from a sample is a lower bound under skew: never start a large input below 2^21 slots (32 MB)
+    if (estimated) target = std::max<u64>(target, 1ull << 21);
+    return std::min(max_log, std::max<u32>(4, ceil_log2_u64(target)));
+}
+
 // Feed every input into one fresh table; on overflow (abort flag) start again 4x larger.
 // slot_out (OPK_DICT): one u32 per row over the concatenation of the inputs.
 static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &inputs, int opk, int tx, u64 hint_distinct,
@@ -494,14 +516,7 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
     if (max_log > MAX_LOG_CAP) return set_err(VB_ERR_TOO_LARGE, "shuffle %llu: %llu rows exceed the device-local limit", (unsigned long long)s->id, (unsigned long long)total);
     bool estimated = false;
     if (!hint_distinct && total > (1ull << 20)) { TRY(estimate_distinct(s, inputs, total, &hint_distinct)); estimated = true; }
-    // Load factor: <= 0.4 while the table (16 B/slot) still fits comfortably in L2 (<= 64 MB), where a
-    // fuller 4-key bucket costs a second dependent probe (2.9 vs 2.2 ms per 2.5e8 rows at load 0.48 vs
-    // 0.24, profiles/r1_micro_v5_lockstep.log); <= 0.5 for bigger tables, which pay DRAM traffic instead.
-    u64 target = hint_distinct ? (hint_distinct * 5) / 2 : std::min<u64>(2 * std::max<u64>(total, 1), 1ull << 21);
-    if (hint_distinct && target > (1ull << 22)) target = 2 * hint_distinct;
-    // an estimate from a sample is a lower bound under skew: never start a large input below 2^21 slots (32 MB)
-    if (estimated) target = std::max<u64>(target, 1ull << 21);
-    u32 log_cap = std::min(max_log, std::max<u32>(4, ceil_log2_u64(target)));
+    u32 log_cap = choose_log_cap(total, hint_distinct, estimated, max_log);
 
     DevBuf ctl(c), stage_a(c), stage_b(c);
     TRY(ctl.alloc(sizeof(TableCtl)));
@@ -895,9 +910,44 @@ static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys,
     CU(cudaSetDevice(c->device));
     KLaunch call(s, -1);
     MapOut &m = s->maps[map_id];
-    if (m.present) { s->st.rows_in -= m.n_rows; free_map(s, m); }   // stage resubmission: overwrite
+    if (m.present) {                                                // stage resubmission: overwrite
+        if (m.in_shared) s->sh_dirty = true;                        // its rows are already in the shared table: rebuild at seal
+        s->st.rows_in -= m.n_rows;
+        free_map(s, m);
+    }
     m.n_rows = n;
-    if (is_reduce_op(s->agg)) {
+    if (is_reduce_op(s->agg) && loc == VB_DEVICE_BORROWED && !combined) {
+        if (!rows && !vals && s->agg != VB_AGG_COUNT && n) return set_err(VB_ERR_INVALID, "values required for this aggregator");
+        std::vector<AggInput> in(1);
+        in[0] = AggInput{rows ? IN_AOS : IN_SOA, rows ? rows : keys, vals, n, VB_DEVICE};
+        if (!s->sh_tab && !s->sh_dirty && n) {       // first borrowed map task: size and create the shared table
+            u64 hint = s->hint;
+            bool estimated = false;
+            const u64 total_guess = n * std::max<u64>(1, s->n_map / std::max<u32>(1, s->world));
+            if (!hint && n > (1ull << 20)) { TRY(estimate_distinct(s, in, total_guess, &hint)); estimated = true; }
+            const u32 max_log = std::min<u32>(MAX_LOG_CAP, std::max<u32>(4, ceil_log2_u64(2 * std::max<u64>(total_guess, 1))));
+            s->sh_log_cap = choose_log_cap(total_guess, hint, estimated, max_log);
+            DevBuf tab(c), ctl(c);
+            TRY(tab.alloc(table_bytes(s->sh_log_cap)));
+            TRY(ctl.alloc(sizeof(TableCtl)));
+            CU(cudaMemsetAsync(ctl.p, 0, sizeof(TableCtl), c->stream));
+            {
+                KLaunch kl(s, K_MISC);
+                const u64 cap = 1ull << s->sh_log_cap;
+                u64 blocks = std::min<u64>((cap + BUCKET + 255) / 256, (u64)c->sm_count * 8);
+                table_init_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(table_at(tab.p, s->sh_log_cap), op_identity(map_opk(s)));
+                TRY(kl.done("table_init_kernel"));
+            }
+            s->sh_max_inserts = (s->sh_log_cap >= max_log) ? ~0ull : ((1ull << s->sh_log_cap) / 10) * 6;
+            s->sh_tab = tab.release();
+            s->sh_ctl = (TableCtl *)ctl.release();
+            s->st.table_slots = std::max<u64>(s->st.table_slots, 1ull << s->sh_log_cap);
+        }
+        if (s->sh_tab && !s->sh_dirty && n)           // asynchronous: checked at seal
+            TRY(launch_hash_agg(s, K_HASH_AGG, in[0].in, map_opk(s), val_tx(s), in[0].a, in[0].b, n, s->sh_tab, s->sh_log_cap, s->sh_ctl,
+                                s->sh_max_inserts, nullptr));
+        m.rows = rows; m.keys = keys; m.vals = vals; m.owned = false; m.in_shared = true;
+    } else if (is_reduce_op(s->agg)) {
         if (!rows && !vals && s->agg != VB_AGG_COUNT && n) return set_err(VB_ERR_INVALID, "values required for this aggregator");
         std::vector<AggInput> in(1);
         in[0] = AggInput{rows ? IN_AOS : IN_SOA, rows ? rows : keys, vals, n, loc == VB_HOST ? VB_HOST : VB_DEVICE};
@@ -1096,25 +1146,67 @@ static int seal_group(vb_shuf *s, const Gathered &g)
 
 // Merge the per-map combined tables of this process into one (ShuffledRdd::compute's
 // merge_combiners loop, shuffled_rdd.rs:154-164, for the partitions held locally).
+// Settle the shared table of the borrowed-input map tasks: wait for the queued kernels, and if the table
+// overflowed or a map id was resubmitted, rebuild it from the (still borrowed) inputs with build_table's
+// restart logic.
+static int settle_shared_table(vb_shuf *s, u64 *n_ins)
+{
+    vb_ctx *c = s->ctx;
+    *n_ins = 0;
+    bool any = false;
+    for (auto &m : s->maps) any |= (m.present && m.in_shared && m.n_rows);
+    bool rebuild = s->sh_dirty;
+    if (s->sh_tab) {
+        TableCtl *h = (TableCtl *)c->h_scratch;
+        CU(cudaMemcpyAsync(h, s->sh_ctl, sizeof(TableCtl), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (h->abort) { rebuild = true; s->st.table_restarts++; }
+        *n_ins = h->n_inserted;
+    }
+    if (rebuild) {
+        dev_free(c, s->sh_tab); dev_free(c, s->sh_ctl);
+        s->sh_tab = nullptr; s->sh_ctl = nullptr;
+        s->sh_dirty = false;
+        if (any) {
+            std::vector<AggInput> in;
+            for (auto &m : s->maps)
+                if (m.present && m.in_shared && m.n_rows)
+                    in.push_back(AggInput{m.rows ? IN_AOS : IN_SOA, m.rows ? m.rows : m.keys, m.vals, m.n_rows, VB_DEVICE});
+            TRY(build_table(s, K_HASH_AGG, in, map_opk(s), val_tx(s), std::max<u64>(s->hint, 2 * (*n_ins)), &s->sh_tab, &s->sh_log_cap, n_ins, nullptr));
+        }
+    }
+    return VB_OK;
+}
+
 static int merge_map_tables(vb_shuf *s, void **tab, u32 *log_cap, u64 *n_ins)
 {
-    std::vector<MapOut *> ts;
-    for (auto &m : s->maps) if (m.present && m.table) ts.push_back(&m);
+    u64 sh_ins = 0;
+    TRY(settle_shared_table(s, &sh_ins));
+    struct T { void *tab; u32 log_cap; u64 ins; };
+    std::vector<T> ts;
+    if (s->sh_tab) ts.push_back(T{s->sh_tab, s->sh_log_cap, sh_ins});
+    for (auto &m : s->maps) if (m.present && m.table) ts.push_back(T{m.table, m.log_cap, m.n_inserted});
+    auto disown = [&]() {
+        s->sh_tab = nullptr;
+        dev_free(s->ctx, s->sh_ctl); s->sh_ctl = nullptr;
+        for (auto &m : s->maps) m.table = nullptr;
+    };
     if (ts.empty()) { *tab = nullptr; *log_cap = 0; *n_ins = 0; return VB_OK; }
     if (ts.size() == 1) {
-        *tab = ts[0]->table; *log_cap = ts[0]->log_cap; *n_ins = ts[0]->n_inserted;
-        ts[0]->table = nullptr;
+        *tab = ts[0].tab; *log_cap = ts[0].log_cap; *n_ins = ts[0].ins;
+        disown();
         return VB_OK;
     }
     std::vector<AggInput> in;
     u64 max_ins = 0;
-    for (auto *m : ts) {
-        const Table mt = table_at(m->table, m->log_cap);
-        in.push_back(AggInput{IN_TABLE, mt.keys, mt.accs, (1ull << m->log_cap) + 1, VB_DEVICE});
-        max_ins = std::max(max_ins, m->n_inserted);
+    for (auto &t : ts) {
+        const Table mt = table_at(t.tab, t.log_cap);
+        in.push_back(AggInput{IN_TABLE, mt.keys, mt.accs, (1ull << t.log_cap) + 1, VB_DEVICE});
+        max_ins = std::max(max_ins, t.ins);
     }
     TRY(build_table(s, K_MERGE, in, merge_opk(s), TX_NONE, std::max<u64>(max_ins, s->hint), tab, log_cap, n_ins, nullptr));
-    for (auto *m : ts) { dev_free(s->ctx, m->table); m->table = nullptr; }
+    for (auto &t : ts) dev_free(s->ctx, t.tab);
+    disown();
     return VB_OK;
 }
 
@@ -1199,6 +1291,8 @@ static int seal_sort(vb_shuf *s, const Gathered &g)
 
 static void release_inputs(vb_shuf *s)
 {
+    dev_free(s->ctx, s->sh_tab); dev_free(s->ctx, s->sh_ctl);
+    s->sh_tab = nullptr; s->sh_ctl = nullptr;
     for (auto &m : s->maps) if (m.present) { u64 n = m.n_rows; free_map(s, m); m.present = true; m.n_rows = n; }
     dev_free(s->ctx, s->gath_keys);
     dev_free(s->ctx, s->gath_vals);
