@@ -256,8 +256,8 @@ def main():
             "clocks": clocks,
             "gpu_launches": agg["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (2.4676e9 if abs(rows_per_launch - 1.25e8) < 1 else None),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of 2), ncu --set full, profiles/r1_ncu_hash_agg_final.txt (1.25e8-row launch, 2^22-slot table: the 64 MB table plus the evict-first stream do not fit L2 entirely; lts__throughput 85 % of peak = the L2 is the saturated unit)",
+                         "traffic": (2.4426e9 if abs(rows_per_launch - 1.25e8) < 1 else None),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of 2), ncu --set full, profiles/r1_ncu_hash_agg_final.txt (1.25e8-row launch, 2^22-slot table: the 64 MB table plus the evict-first stream do not fit L2 entirely; lts__throughput 87 % of peak = the L2 is the saturated unit)",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel": "hash_agg_kernel<IN_AOS,OPK_ADD_U64>",
                          "rows_per_launch": rows_per_launch, "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
                          "step_share": agg["hot_ms"] / max(ms_total, 1e-9),
