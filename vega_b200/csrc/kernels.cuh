@@ -660,11 +660,12 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
         for (int i = 0; i < RPS_ITEMS; ++i) {
             const u32 d = dig[i];
             const u32 peers = warp_match_digit<BITS>(d);
-            const u32 base = cnt[warp][d];
-            __syncwarp();
-            if (lane == (u32)(__ffs(peers) - 1)) cnt[warp][d] = base + __popc(peers);
-            __syncwarp();
+            const u32 leader = (u32)(__ffs(peers) - 1);
+            u32 base = 0;
+            if (lane == leader) { base = cnt[warp][d]; cnt[warp][d] = base + __popc(peers); }   // only the group leader touches smem
+            base = __shfl_sync(0xffffffffu, base, leader);
             rank[i] = (unsigned short)(base + __popc(peers & lt));
+            __syncwarp();                                                       // orders this round's store before the next round's load
         }
         __syncthreads();                                                        // B1: warp counts complete
         // thread d: exclusive scan of digit d over the warps, then a block-wide exclusive scan over the digits
@@ -685,17 +686,19 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
             u32 excl = incl - total;
             for (u32 w = 0; w < warp; ++w) excl += wtot[w];
             dbase[tid] = excl;
+#pragma unroll
+            for (int w = 0; w < RPS_WARPS; ++w) cnt[w][tid] += excl;            // cnt[w][d] = tile position of warp w's first row of digit d
             if (tid < NB) {
                 const u32 ro = run_off[tid];
                 gbase[tid] = ro - excl;
                 run_off[tid] = ro + total;
             }
         }
-        __syncthreads();                                                        // B3: dbase / gbase visible
+        __syncthreads();                                                        // B3: positions / gbase visible
 #pragma unroll
         for (int i = 0; i < RPS_ITEMS; ++i) {
             const u32 d = dig[i];
-            const u32 pos = dbase[d] + cnt[warp][d] + rank[i];
+            const u32 pos = cnt[warp][d] + rank[i];
             stage_keys[pos] = key[i];
             if (HAS_VAL) stage_vals[pos] = val[i];
             if (d < NB) {                                   // rows with d == NB (invalid) sit past n_valid
