@@ -501,3 +501,28 @@ def test_shared_table_of_borrowed_map_tasks(sc):
     gotf = gpu_reduce_parts(sc.parallelize((tk, fv), 4).reduce_by_key("min", 3))
     wantf = oracle_reduce("min", keys, fv.cpu().numpy(), 4, 3, "f64")
     assert [{k & (2 ** 64 - 1): v for k, v in d.items()} for d in gotf] == wantf
+
+
+@pytest.mark.parametrize("kind", ["small_u64", "small_i64_neg", "all_equal", "f64_narrow", "high_bits_only"])
+def test_sort_skips_constant_digits(sc, kind):
+    """Radix digits on which every key agrees are skipped; the result must still equal the stable oracle sort."""
+    rng = np.random.default_rng(17)
+    n = 50_000
+    kdt = "u64"
+    if kind == "small_u64":
+        keys = rng.integers(0, 1000, n).astype(np.uint64)
+    elif kind == "small_i64_neg":
+        keys = rng.integers(-300, 300, n).astype(np.int64); kdt = "i64"
+    elif kind == "all_equal":
+        keys = np.full(n, 12345, dtype=np.uint64)
+    elif kind == "f64_narrow":
+        keys = rng.integers(-50, 50, n).astype(np.float64) * 0.5; kdt = "f64"
+    else:
+        keys = rng.integers(0, 256, n).astype(np.uint64) << np.uint64(56)
+    vals = np.arange(n, dtype=np.uint64)
+    ok, ov, ps = O.sort_by_key(keys, vals, 4, kdt)
+    rdd = sc.parallelize((keys, vals), 3).sort_by_key(4)
+    k, v = rdd.collect()
+    assert (k == ok).all() and (v == ov).all()
+    launches = rdd.stats()["kernels"]["rp_scatter"]["launches"]
+    assert launches <= {"small_u64": 2, "small_i64_neg": 8, "all_equal": 1, "f64_narrow": 8, "high_bits_only": 1}[kind]

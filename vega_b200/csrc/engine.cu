@@ -1258,10 +1258,32 @@ static int seal_sort(vb_shuf *s, const Gathered &g)
     TRY(hist.alloc(plan.hist_bytes()));
     u64 *src_k = nullptr, *src_v = nullptr, *dst_k = ka.as<u64>(), *dst_v = va.as<u64>();
     constexpr u32 SORT_PASSES = (64 + RP_SORT_BITS - 1) / RP_SORT_BITS;
+    // digits on which all keys agree are skipped (e.g. 32-bit-range keys take 4 passes, not 8)
+    u64 varying = ~0ull;
+    {
+        DevBuf bits(c);
+        TRY(bits.alloc(16));
+        const unsigned long long init[2] = {0ull, ~0ull};
+        CU(cudaMemcpyAsync(bits.p, init, 16, cudaMemcpyHostToDevice, c->stream));
+        KLaunch kl(s, K_MISC);
+        key_bits_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(g.rows ? g.rows : g.keys, g.rows ? 2 : 1, n, tx, (unsigned long long *)bits.p);
+        TRY(kl.done("key_bits_kernel"));
+        u64 *h = (u64 *)c->h_scratch;
+        CU(cudaMemcpyAsync(h, bits.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        varying = h[0] ^ h[1];
+    }
+    bool first = true;
+    u32 done = 0;
     for (u32 p = 0; p < SORT_PASSES; ++p) {
+        const u64 dmask = (u64)((1u << RP_SORT_BITS) - 1) << (RP_SORT_BITS * p);
+        const bool last_chance = (p + 1 == SORT_PASSES) && done == 0;      // at least one pass: it also copies the rows out
+        if (!(varying & dmask) && !last_chance) continue;
+        ++done;
         Loader ld;
-        if (p == 0) ld = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
+        if (first) ld = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
         else ld = Loader{LD_SOA64, src_k, has_val ? src_v : nullptr, 0};
+        first = false;
         Digit dg{};
         dg.mode = DG_BITS; dg.shift = RP_SORT_BITS * p; dg.mask = (1u << RP_SORT_BITS) - 1; dg.tx = tx;
         if (has_val) TRY((radix_pass<u64, true>(s, ld, dg, n, dst_k, dst_v, hist.as<u32>(), plan)));
