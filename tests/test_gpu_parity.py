@@ -526,3 +526,82 @@ def test_sort_skips_constant_digits(sc, kind):
     assert (k == ok).all() and (v == ov).all()
     launches = rdd.stats()["kernels"]["rp_scatter"]["launches"]
     assert launches <= {"small_u64": 2, "small_i64_neg": 8, "all_equal": 1, "f64_narrow": 8, "high_bits_only": 1}[kind]
+
+
+def _big_gpu():
+    import torch
+    return torch.cuda.get_device_properties(0).total_memory >= 120 * 2 ** 30
+
+
+def test_group_by_key_full_size_properties(sc):
+    """north_star size for group_by_key (1e9 pairs, 1e6 keys, 8 partitions) through size-independent properties:
+    all N values come back, every partition's CSR is consistent, and for sampled keys the value list equals
+    the brute-force filter of the input IN INPUT ORDER."""
+    import torch
+    if not _big_gpu():
+        pytest.skip("needs a 180 GB GPU")
+    n, D, R = 1_000_000_000, 1_000_000, 8
+    rows = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=0, n=n, mode="uniform", n_distinct=D, seed_k=1, seed_v=2)
+    sh = sc.make_rdd(rows, 8).group_by_key(R)._run()
+    tot_keys = tot_vals = 0
+    checked = 0
+    for r in range(R):
+        nk, nv = sh.reduce_size(r)
+        tot_keys += nk; tot_vals += nv
+        if r in (0, 5):
+            k = torch.empty(nk, dtype=torch.int64, device="cuda")
+            o = torch.empty(nk + 1, dtype=torch.int64, device="cuda")
+            v = torch.empty(nv, dtype=torch.int64, device="cuda")
+            sh.reduce_device(r, out_keys=k, out_offs=o, out_vals=v)
+            assert int(o[0]) == 0 and int(o[-1]) == nv and bool((o[1:] >= o[:-1]).all())
+            assert int(torch.unique(k).numel()) == nk
+            for j in (0, nk // 2, nk - 1):
+                key = int(k[j])
+                assert O.get_partition(key & (2 ** 64 - 1), R) == r
+                brute = rows[:, 1][rows[:, 0] == key]              # input order
+                got = v[int(o[j]):int(o[j + 1])]
+                assert got.numel() == brute.numel() and bool((got == brute).all())
+                checked += 1
+            del k, o, v
+    assert tot_keys == D and tot_vals == n and checked == 6
+    sh.free()
+    del rows
+    torch.cuda.empty_cache()
+
+
+def test_sort_by_key_full_size_properties(sc):
+    """configs[2]: sort_by_key of 1e9 64-bit keys into 8 partitions: sorted, a permutation of the input
+    (sum and xor checksums), partitions are contiguous key ranges that never split a key."""
+    import torch
+    if not _big_gpu():
+        pytest.skip("needs a 180 GB GPU")
+    n, R = 1_000_000_000, 8
+    keys = torch.empty(n, dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_keys=keys, first=0, n=n, mode="unique", rank_base=3)
+    want_sum = int(keys.sum().item())
+    want_xor = 0
+    for chunk in keys.split(1 << 27):
+        want_xor ^= int(np.bitwise_xor.reduce(chunk.cpu().numpy()))
+    sh = sc.parallelize(keys, 8).sort(R)._run()
+    got_sum, got_xor, prev_last, tot = 0, 0, None, 0
+    for r in range(R):
+        nk, _ = sh.reduce_size(r)
+        out = torch.empty(nk, dtype=torch.int64, device="cuda")
+        sh.reduce_device(r, out_keys=out)
+        tot += nk
+        # the keys travel as an int64 tensor, i.e. key dtype i64: signed order
+        u = out
+        assert bool((u[1:] >= u[:-1]).all())
+        if prev_last is not None and nk:
+            assert int(u[0]) > prev_last                         # contiguous ranges, no key split across partitions
+        if nk:
+            prev_last = int(u[-1])
+        got_sum = (got_sum + int(out.sum().item())) % (1 << 64)
+        for chunk in out.split(1 << 27):
+            got_xor ^= int(np.bitwise_xor.reduce(chunk.cpu().numpy()))
+        del out, u
+    assert tot == n and got_sum == want_sum % (1 << 64) and got_xor == want_xor
+    sh.free()
+    del keys
+    torch.cuda.empty_cache()

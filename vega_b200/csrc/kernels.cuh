@@ -600,12 +600,12 @@ struct RemoteDst {
 // into the destination GPUs' HBM (st.global on peer-mapped addresses), so the NVLink transfer overlaps
 // ranking/staging of the following tiles.
 template <typename KeyT, bool HAS_VAL, int LDM, int DGM, int BITS, bool REMOTE = false>
-__global__ void __launch_bounds__(RPS_THREADS, (RPS_THREADS > 512 ? 1 : 2))
+__global__ void __launch_bounds__(RPS_THREADS, (RPS_THREADS > 512 ? 1 : RPS_THREADS > 256 ? 2 : 4))
 rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__restrict__ part_off, u32 num_parts,
                   KeyT *__restrict__ out_keys, u64 *__restrict__ out_vals, RemoteDst rd)
 {
     constexpr int NB = 1 << BITS;
-    static_assert(NB + 1 <= RPS_THREADS, "one thread per digit in the tile scan");
+    static_assert(NB <= RPS_THREADS, "one thread per digit in the tile scan");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *stage_vals = (u64 *)smem_raw;                                       // [RP_TILE] if HAS_VAL
     KeyT *stage_keys = (KeyT *)(smem_raw + (HAS_VAL ? RP_TILE * 8 : 0));     // [RP_TILE]
@@ -668,9 +668,10 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
             __syncwarp();                                                       // orders this round's store before the next round's load
         }
         __syncthreads();                                                        // B1: warp counts complete
-        // thread d: exclusive scan of digit d over the warps, then a block-wide exclusive scan over the digits
+        // thread d < NB: exclusive scan of digit d over the warps, then a block-wide exclusive scan over the digits;
+        // the "invalid" bin NB sits after all valid rows and is handled by one extra thread below
         u32 total = 0;
-        if (tid <= NB) {
+        if (tid < NB) {
 #pragma unroll
             for (int w = 0; w < RPS_WARPS; ++w) { const u32 c = cnt[w][tid]; cnt[w][tid] = total; total += c; }
         }
@@ -682,16 +683,19 @@ rp_scatter_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, const u32 *__re
         }
         if (lane == 31) wtot[warp] = incl;
         __syncthreads();                                                        // B2: warp totals visible
-        if (tid <= NB) {
+        if (tid < NB) {
             u32 excl = incl - total;
             for (u32 w = 0; w < warp; ++w) excl += wtot[w];
             dbase[tid] = excl;
 #pragma unroll
             for (int w = 0; w < RPS_WARPS; ++w) cnt[w][tid] += excl;            // cnt[w][d] = tile position of warp w's first row of digit d
-            if (tid < NB) {
-                const u32 ro = run_off[tid];
-                gbase[tid] = ro - excl;
-                run_off[tid] = ro + total;
+            const u32 ro = run_off[tid];
+            gbase[tid] = ro - excl;
+            run_off[tid] = ro + total;
+            if (tid == NB - 1) {                                                // rows of the invalid bin follow the valid ones
+                u32 nv = excl + total;
+                dbase[NB] = nv;
+                for (int w = 0; w < RPS_WARPS; ++w) { const u32 c = cnt[w][NB]; cnt[w][NB] = nv; nv += c; }
             }
         }
         __syncthreads();                                                        // B3: positions / gbase visible
