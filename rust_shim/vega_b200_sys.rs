@@ -33,6 +33,20 @@ extern "C" {
     pub fn vb_join_size(left: *mut vb_shuf, right: *mut vb_shuf, reduce_id: u32, n_out: *mut u64) -> i32;
     pub fn vb_join(left: *mut vb_shuf, right: *mut vb_shuf, reduce_id: u32, out_k: *mut c_void, out_v: *mut c_void,
                    out_w: *mut c_void, dst_loc: i32) -> i32;
+    // N1: bincode blobs (the payload format of SHUFFLE_CACHE)
+    pub fn vb_shuffle_reduce_blob_size(s: *mut vb_shuf, reduce_id: u32, n_bytes: *mut u64) -> i32;
+    pub fn vb_shuffle_reduce_blob(s: *mut vb_shuf, reduce_id: u32, out_blob: *mut c_void, dst_loc: i32) -> i32;
+    pub fn vb_shuffle_map_blob(s: *mut vb_shuf, map_id: u32, blob: *const c_void, n_bytes: u64, src_loc: i32) -> i32;
+    // one process per GPU: pack + all-to-all-v, or the fused exchange over peer memory
+    pub fn vb_shuffle_set_dist(s: *mut vb_shuf, rank: u32, world: u32) -> i32;
+    pub fn vb_shuffle_export_prepare(s: *mut vb_shuf, counts: *mut u64) -> i32;
+    pub fn vb_shuffle_export_buffers(s: *mut vb_shuf, keys_dev: *mut *mut c_void, vals_dev: *mut *mut c_void) -> i32;
+    pub fn vb_shuffle_import(s: *mut vb_shuf, keys_dev: *const c_void, vals_dev: *const c_void, counts: *const u64) -> i32;
+    pub fn vb_ctx_arena_reserve(ctx: *mut vb_ctx, bytes: u64, handle_out: *mut c_void, generation: *mut u64) -> i32;
+    pub fn vb_ctx_peer_open(ctx: *mut vb_ctx, peer_rank: u32, handle: *const c_void, generation: u64, is_self: i32) -> i32;
+    pub fn vb_shuffle_export_counts(s: *mut vb_shuf, counts: *mut u64) -> i32;
+    pub fn vb_shuffle_export_direct(s: *mut vb_shuf, dst_row_offset: *const u64, dst_total_rows: *const u64) -> i32;
+    pub fn vb_shuffle_import_arena(s: *mut vb_shuf, counts: *const u64) -> i32;
     pub fn vb_shuffle_free(s: *mut vb_shuf) -> i32;
     pub fn vb_last_error() -> *const c_char;
     pub fn vb_get_partition(key: u64, key_width: u32, n_reduce: u32) -> u32;
