@@ -98,3 +98,32 @@ def test_host_mirror_argument_checks():
     assert c.key_width == 4 and c.code == 1 and c.n == 6
     c = _Col(np.zeros((5, 2), dtype=np.uint64), allow_rows=True)
     assert c.rows and c.n == 5
+
+
+def test_python_constants_match_header_enums():
+    """vega_b200/_lib.py mirrors the enums of include/vega_b200.h by value."""
+    from vega_b200 import _lib as L
+    src = open(os.path.join(ROOT, "include", "vega_b200.h")).read()
+    vals = {}
+    for body in re.findall(r"enum\s+\w+\s*\{([^}]*)\}", src):
+        nxt = 0
+        for item in body.split(","):
+            item = re.sub(r"/\*.*?\*/", "", item, flags=re.S).strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, v = [x.strip() for x in item.split("=")]
+                nxt = int(v, 0)
+            else:
+                name = item
+            vals[name] = nxt
+            nxt += 1
+    for name, v in vals.items():
+        if hasattr(L, name):
+            assert getattr(L, name) == v, name
+    for name in ("VB_OK", "VB_ERR_CUDA", "VB_U64", "VB_F64", "VB_AGG_GROUP", "VB_AGG_SORT", "VB_PART_RANGE", "VB_DEVICE_BORROWED", "VB_GEN_UNIQUE"):
+        assert name in vals and getattr(L, name) == vals[name]
+    # struct layout of vb_stats: 9 u64 + 3 doubles in header order
+    assert ctypes.sizeof(L.vb_stats) == 12 * 8
+    fields = re.findall(r"\b(uint64_t|double)\s+(\w+);", src[src.index("typedef struct vb_stats"):src.index("} vb_stats;")])
+    assert [f for _, f in fields] == [f for f, _ in L.vb_stats._fields_]
