@@ -11,7 +11,10 @@
  * tests/test_rdd.rs:285-322,387-456,484-521,675-699) in tests/test_oracle_golden.py.
  * The *partition placement* hash (MetroHash64_1, third-party crate fasthash 0.4.0,
  * Cargo.toml:20, source not under /root/reference) is restated from the published
- * algorithm and is "parity unpinned" — the reference's only test at that boundary
+ * algorithm and pinned to MetroHash's published known-answer vector (63-byte test key,
+ * seeds 0 and 1: 658F044F5C730E40 / AE49EBB0A856537B — every tail branch is exercised).
+ * What stays "parity unpinned" is the binding fasthash::MetroHasher == metrohash64_1(seed 0)
+ * over the bytes Rust's Hash impl writes: the reference's only test at that boundary
  * (src/partitioner.rs:63-82) asserts nothing about hash values.  No observable
  * result (collected multiset of (K,C), ordered value lists) depends on it.
  *
