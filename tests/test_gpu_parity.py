@@ -605,3 +605,39 @@ def test_sort_by_key_full_size_properties(sc):
     sh.free()
     del keys
     torch.cuda.empty_cache()
+
+
+def test_partition_first_for_tables_larger_than_l2(sc):
+    """With > 6.7e6 distinct keys the table passes 2^24 slots (256 MB > L2): rows are first radix-partitioned by the
+    top bits of the slot hash so each table region is filled while L2-resident.  Results must not change."""
+    import torch
+    n_half = 5_000_000
+    a = torch.empty((n_half, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=a, first=0, n=n_half, mode="unique", rank_base=0, seed_v=2)
+    b = torch.empty((n_half, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=b, first=0, n=n_half, mode="unique", rank_base=1_000_000, seed_v=7)   # 4e6 keys overlap with a
+    rows = torch.cat([a, b]).contiguous()
+    host = rows.cpu().numpy().view(np.uint64)
+    keys, vals = host[:, 0].copy(), host[:, 1].copy()
+    for op in ("sum", "max"):
+        rdd = sc.make_rdd(rows, 4).reduce_by_key(op, 5)
+        got = gpu_reduce_parts(rdd)
+        assert rdd.stats()["table_slots"] >= 1 << 24
+        got = [{k & (2 ** 64 - 1): v & (2 ** 64 - 1) for k, v in d.items()} for d in got]
+        assert got == oracle_reduce(op, keys, vals, 4, 5)
+    # host-copied (per-map table) path through build_table as well
+    rdd = sc.parallelize((torch.from_numpy(keys.view(np.int64)).cuda().clone(), torch.from_numpy(vals.view(np.int64)).cuda().clone()), 2)
+    sh = vb.Shuffle(sc, 2, 3, 0, 0, 4, hint=6_000_000)          # count, explicit hint → 2^24 slots
+    st = vb.slice_starts(len(keys), 2)
+    for m in range(2):
+        sh.map(m, vb.rdd._Col(rdd.keys.owner[int(st[m]):int(st[m + 1])].clone()), None, 0, int(st[m + 1] - st[m]))
+    sh.seal()
+    got = {}
+    for r in range(3):
+        k, c = sh.reduce(r)
+        got.update(zip((k.view(np.uint64)).tolist(), c.tolist()))
+    want = {}
+    for d in oracle_reduce("count", keys, None, 2, 3):
+        want.update(d)
+    assert got == want
+    sh.free()

@@ -498,6 +498,28 @@ static u32 choose_log_cap(u64 total, u64 hint_distinct, bool estimated, u32 max_
     return std::min(max_log, std::max<u32>(4, ceil_log2_u64(target)));
 }
 
+// Tables of 2^24 slots (256 MB) and more do not fit the 126 MB L2: every probe and every RED becomes a random
+// DRAM access (57 ms per 1e9 rows at 1e7 keys, 86 ms at 1e8 — profiles/r1_cardinality_sweep_before_partitioning.jsonl).
+// Such inputs are first radix-partitioned by the top bits of the slot hash (one stable 8-bit pass, ~10 ms per 1e9
+// rows), so that consecutive tiles of hash_agg_kernel all probe the same <= 32 MB region of the table, which then
+// stays L2-resident while it is being filled.  Reduce ops on device-resident rows only (the dictionary of group ops
+// must keep row order, host inputs are PCIe-bound anyway).  VEGA_B200_NO_PARTITION=1 disables it.
+struct PassPlan;
+template <typename KeyT, bool HAS_VAL> static PassPlan plan_pass(vb_ctx *c, u64 n, int bits);
+template <typename KeyT, bool HAS_VAL>
+static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist, const PassPlan &plan);
+
+constexpr u32 PARTITION_MIN_LOG_CAP = 24;
+
+static bool want_partition(int in, int opk, u32 log_cap, u64 n)
+{
+    static const bool off = getenv("VEGA_B200_NO_PARTITION") != nullptr;
+    return !off && opk != OPK_DICT && (in == IN_AOS || in == IN_SOA) && log_cap >= PARTITION_MIN_LOG_CAP && n >= (1ull << 22);
+}
+
+static int launch_hash_agg_partitioned(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
+                                       u32 log_cap, TableCtl *ctl, u64 mi);
+
 // Feed every input into one fresh table; on overflow (abort flag) start again 4x larger.
 // slot_out (OPK_DICT): one u32 per row over the concatenation of the inputs.
 static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &inputs, int opk, int tx, u64 hint_distinct,
@@ -540,7 +562,9 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
         u64 row_base = 0;
         for (auto &in : inputs) {
             if (in.n == 0) continue;
-            if (in.loc != VB_HOST) {
+            if (in.loc != VB_HOST && !slot_out && want_partition(in.in, opk, log_cap, in.n)) {
+                TRY(launch_hash_agg_partitioned(s, klass, in.in, opk, tx, in.a, in.b, in.n, tab.p, log_cap, ctl.as<TableCtl>(), max_inserts));
+            } else if (in.loc != VB_HOST) {
                 TRY(launch_hash_agg(s, klass, in.in, opk, tx, in.a, in.b, in.n, tab.p, log_cap, ctl.as<TableCtl>(),
                                     max_inserts, slot_out ? slot_out + row_base : nullptr));
             } else {
@@ -597,7 +621,8 @@ struct PassPlan {
     X(LD_SOA64, DG_BITS, RP_SORT_BITS) X(LD_AOS64, DG_BITS, RP_SORT_BITS)                                       \
     X(LD_KEY32_VAL_SOA, DG_BITS, RP_SORT_BITS) X(LD_KEY32_VAL_AOS, DG_BITS, RP_SORT_BITS)                       \
     X(LD_SOA64, DG_BUCKET, 8) X(LD_TABLE_KV, DG_BUCKET, 8) X(LD_TABLE_KI, DG_BUCKET, 8)                         \
-    X(LD_SOA64, DG_DEST, 8) X(LD_AOS64, DG_DEST, 8) X(LD_TABLE_KV, DG_DEST, 8)
+    X(LD_SOA64, DG_DEST, 8) X(LD_AOS64, DG_DEST, 8) X(LD_TABLE_KV, DG_DEST, 8)                                 \
+    X(LD_SOA64, DG_HASHTOP, 8) X(LD_AOS64, DG_HASHTOP, 8)
 
 template <typename KeyT, int LDM> constexpr bool rp_key_ok()
 {
@@ -711,6 +736,26 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
         TRY(kl.done("rp_scatter_kernel"));
     }
     return VB_OK;
+}
+
+static int launch_hash_agg_partitioned(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
+                                       u32 log_cap, TableCtl *ctl, u64 mi)
+{
+    vb_ctx *c = s->ctx;
+    const u32 pbits = std::min<u32>(8, log_cap - 21);          // regions of <= 2^21 slots (32 MB) while 256 bins suffice
+    DevBuf tk(c), tv(c), hist(c);
+    TRY(tk.alloc(n * 8));
+    TRY(tv.alloc(n * 8));
+    PassPlan plan = plan_pass<u64, true>(c, n, 8);
+    TRY(hist.alloc(plan.hist_bytes()));
+    Loader ld = (in == IN_AOS) ? Loader{LD_AOS64, a, nullptr, 0} : Loader{LD_SOA64, a, b, 0};
+    Digit dg{};
+    dg.mode = DG_HASHTOP;
+    dg.shift = 64 - pbits;
+    dg.mask = (1u << pbits) - 1;
+    TRY((radix_pass<u64, true>(s, ld, dg, n, tk.as<u64>(), tv.as<u64>(), hist.as<u32>(), plan)));
+    // stream-ordered frees: the buffers outlive the kernels queued on c->stream
+    return launch_hash_agg(s, klass, IN_SOA, opk, tx, tk.as<u64>(), tv.as<u64>(), n, tab, log_cap, ctl, mi, nullptr);
 }
 
 // Copy the start offset of each of the first nb digits plus the total to the host: out[nb+1].
@@ -943,9 +988,14 @@ static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys,
             s->sh_ctl = (TableCtl *)ctl.release();
             s->st.table_slots = std::max<u64>(s->st.table_slots, 1ull << s->sh_log_cap);
         }
-        if (s->sh_tab && !s->sh_dirty && n)           // asynchronous: checked at seal
-            TRY(launch_hash_agg(s, K_HASH_AGG, in[0].in, map_opk(s), val_tx(s), in[0].a, in[0].b, n, s->sh_tab, s->sh_log_cap, s->sh_ctl,
-                                s->sh_max_inserts, nullptr));
+        if (s->sh_tab && !s->sh_dirty && n) {         // asynchronous: checked at seal
+            if (want_partition(in[0].in, map_opk(s), s->sh_log_cap, n))
+                TRY(launch_hash_agg_partitioned(s, K_HASH_AGG, in[0].in, map_opk(s), val_tx(s), in[0].a, in[0].b, n, s->sh_tab, s->sh_log_cap,
+                                                s->sh_ctl, s->sh_max_inserts));
+            else
+                TRY(launch_hash_agg(s, K_HASH_AGG, in[0].in, map_opk(s), val_tx(s), in[0].a, in[0].b, n, s->sh_tab, s->sh_log_cap, s->sh_ctl,
+                                    s->sh_max_inserts, nullptr));
+        }
         m.rows = rows; m.keys = keys; m.vals = vals; m.owned = false; m.in_shared = true;
     } else if (is_reduce_op(s->agg)) {
         if (!rows && !vals && s->agg != VB_AGG_COUNT && n) return set_err(VB_ERR_INVALID, "values required for this aggregator");

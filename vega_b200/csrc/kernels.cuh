@@ -427,10 +427,11 @@ VB_D bool rp_load_key(const Loader &ld, u64 i, KeyT &key, u64 pol)
     }
 }
 
-enum : int { DG_BITS = 0, DG_BUCKET = 1, DG_DEST = 2 };
+enum : int { DG_BITS = 0, DG_BUCKET = 1, DG_DEST = 2, DG_HASHTOP = 3 };
 
 // Which bin a key goes to.  DG_BITS: radix digit of the (order-transformed) key.  DG_BUCKET:
 // digit of HashPartitioner::get_partition(key).  DG_DEST: owning rank = partition % world.
+// DG_HASHTOP: top bits of slot_hash(key) — pre-partitions rows so a table larger than L2 is visited region by region.
 struct Digit {
     int mode;
     u32 shift, mask;
@@ -446,6 +447,9 @@ VB_D u32 rp_digit(const Digit &dg, KeyT key)
     if constexpr (DGM == DG_BITS) {
         u64 k = (sizeof(KeyT) == 8) ? tx_fwd((u64)key, dg.tx) : (u64)key;
         return (u32)(k >> dg.shift) & dg.mask;
+    } else if constexpr (DGM == DG_HASHTOP) {
+        // top bits of the table's slot hash: rows of one digit probe one contiguous region of the table
+        return (u32)(slot_hash((u64)key) >> dg.shift) & dg.mask;
     } else {
         u32 b = get_partition((u64)key, dg.key_width, dg.fm);
         if constexpr (DGM == DG_DEST) return fastmod(b, dg.fm_world);

@@ -163,6 +163,7 @@ class Shuffle:
         self.sc, self._lib = sc, sc._lib
         self.n_map, self.n_reduce, self.agg, self.vcode, self.kcode = n_map, n_reduce, agg, vcode, kcode
         self.has_payload = True
+        self._keepalive = []      # owners of VB_DEVICE_BORROWED inputs: the library reads them until seal
         h = ctypes.c_void_p()
         part = L.VB_PART_RANGE if agg == L.VB_AGG_SORT else L.VB_PART_HASH_METRO64
         L.check(self._lib.vb_shuffle_create(sc._h, sc.new_shuffle_id(), n_map, n_reduce, kcode, vcode, agg, part, ctypes.byref(h)))
@@ -178,6 +179,8 @@ class Shuffle:
     def map(self, map_id, keys, vals, start, stop):
         """ShuffleMapTask::run for one map partition = rows [start, stop) of the parent."""
         n = stop - start
+        if keys.loc == L.VB_DEVICE_BORROWED:
+            self._keepalive.append((keys.owner, vals.owner if vals is not None else None))
         if keys.rows:
             L.check(self._lib.vb_shuffle_map_aos(self._h, map_id, keys.at(start), n, keys.loc))
         else:
@@ -187,6 +190,7 @@ class Shuffle:
 
     def seal(self):
         L.check(self._lib.vb_shuffle_seal(self._h))
+        self._keepalive = []
 
     def reduce_size(self, r):
         nk, nv = ctypes.c_uint64(), ctypes.c_uint64()
