@@ -30,6 +30,8 @@
  * device memory is library-owned unless passed in as VB_DEVICE*.  Entry points may be called
  * concurrently from arbitrary OS threads (vega runs map tasks on a tokio blocking pool,
  * src/scheduler/local_scheduler.rs:336-352); device work of one context is serialised.
+ * Device work runs on the context's own stream (vb_ctx_stream): device buffers handed in must be complete
+ * (producer stream synchronised) before the call; results are complete when a call returns.
  * There is NO CPU fallback: without a CUDA device every compute entry returns VB_ERR_CUDA.
  *
  * Rows are POD (K,V) with 64-bit K and V; `Aggregator` closures (src/aggregator.rs:8-16) are

@@ -45,6 +45,9 @@ class _Col:
             if code is None:
                 raise TypeError(f"unsupported tensor dtype {x.dtype}")
             self.loc = L.VB_DEVICE_BORROWED if x.is_cuda else L.VB_HOST
+            if x.is_cuda:
+                # the library launches on its own stream: whatever produced this tensor on torch's stream must be done
+                torch.cuda.current_stream(x.device).synchronize()
             self.ptr = x.data_ptr()
             shape = tuple(x.shape)
         else:
