@@ -29,6 +29,16 @@ def _is_torch(x):
     return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
 
 
+def _sync_torch(*tensors):
+    """The library runs on its own stream: pending torch work on buffers it is about to touch must be done
+    (torch's caching allocator may hand out memory whose previous user is still running on torch's stream)."""
+    for t in tensors:
+        if t is not None and _is_torch(t) and t.is_cuda:
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
+            return
+
+
 class _Col:
     """One 64-bit column (or an (n,2) AoS row block): pointer + location + dtype code."""
 
@@ -141,6 +151,7 @@ class Context:
                   rank_base=0, seed_k=1, seed_v=2, zipf_s=0.0):
         """Fill device buffers (torch CUDA tensors) with the synthetic workload of SURVEY.md §8(d)."""
         m = {"uniform": L.VB_GEN_UNIFORM, "zipf": L.VB_GEN_ZIPF, "unique": L.VB_GEN_UNIQUE}[mode]
+        _sync_torch(out_rows, out_keys, out_vals)
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         L.check(self._lib.vb_gen_pairs(self._h, p(out_rows), p(out_keys), p(out_vals), first, n, m, n_distinct,
                                        rank_base, seed_k, seed_v, float(zipf_s)))
@@ -220,6 +231,7 @@ class Shuffle:
 
     def reduce_device(self, r, out_keys=None, out_comb=None, out_offs=None, out_vals=None):
         """Same, into caller-provided torch CUDA tensors (any may be None)."""
+        _sync_torch(out_keys, out_comb, out_offs, out_vals)
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         L.check(self._lib.vb_shuffle_reduce(self._h, r, p(out_keys), p(out_comb), p(out_offs), p(out_vals), L.VB_DEVICE))
 
