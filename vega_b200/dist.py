@@ -66,6 +66,10 @@ class CudaEngine:
         return counts, keys, vals
 
     def import_(self, sh, keys, vals, counts):
+        import torch
+        if keys.is_cuda:
+            # NCCL collectives are stream-ordered on torch's stream; the library reads on its own stream
+            torch.cuda.current_stream(keys.device).synchronize()
         sh._imported = (keys, vals)            # keep the tensors alive until seal
         c = (ctypes.c_uint64 * len(counts))(*counts)
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
