@@ -89,3 +89,23 @@ def test_map_block_assignment_is_contiguous_and_complete():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
         owned = sorted(p for r in range(world) for p in owned_partitions(r, world, 13))
         assert owned == list(range(13))
+
+
+def test_p2p_arena_layout_is_a_partition_of_every_arena():
+    """Fused exchange: the blocks the ranks write into one arena must tile it exactly, source-rank major."""
+    from vega_b200.dist import p2p_layout
+    rng = np.random.default_rng(4)
+    for world in (2, 3, 8):
+        allc = rng.integers(0, 1000, (world, world)).tolist()
+        layouts = [p2p_layout(allc, r) for r in range(world)]
+        for dst in range(world):
+            total = layouts[0][0][dst]
+            assert all(l[0][dst] == total for l in layouts) and total == sum(allc[src][dst] for src in range(world))
+            blocks = sorted((layouts[src][1][dst], allc[src][dst], src) for src in range(world))
+            pos = 0
+            for off, cnt, src in blocks:
+                assert off == pos            # contiguous, no overlap, no gap
+                pos += cnt
+            assert pos == total
+            assert [b[2] for b in blocks if b[1]] == sorted(b[2] for b in blocks if b[1])   # source-rank major
+            assert layouts[dst][2] == [allc[src][dst] for src in range(world)]

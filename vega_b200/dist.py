@@ -83,6 +83,17 @@ class CudaEngine:
         return sh.reduce(r)
 
 
+def p2p_layout(allc, rank):
+    """Arena layout of the fused exchange from the all-gathered count matrix allc[src][dst]:
+    (total rows each rank receives, row offset of `rank`'s block inside every destination's arena,
+    rows `rank` receives from every source).  Blocks are source-rank major, so the arena order is map-id order."""
+    world = len(allc)
+    total_recv = [sum(allc[src][dst] for src in range(world)) for dst in range(world)]
+    my_off = [sum(allc[src][dst] for src in range(rank)) for dst in range(world)]
+    recv_counts = [allc[src][rank] for src in range(world)]
+    return total_recv, my_off, recv_counts
+
+
 def p2p_exchange(engine, sh, rank, world, group=None, stats=None):
     """Fused exchange of a GROUP/COGROUP shuffle: the partition kernel of every rank stores its rows straight
     into the owners' HBM (CUDA IPC peer mappings over NVLink) — see include/vega_b200.h.  torch.distributed only
@@ -100,8 +111,7 @@ def p2p_exchange(engine, sh, rank, world, group=None, stats=None):
     counts = [int(c) for c in counts]
     allc = [None] * world
     dist.all_gather_object(allc, counts, group=group)            # allc[src][dst]
-    total_recv = [sum(allc[src][dst] for src in range(world)) for dst in range(world)]
-    my_off = [sum(allc[src][dst] for src in range(rank)) for dst in range(world)]
+    total_recv, my_off, recv_counts = p2p_layout(allc, rank)
     handle = (ctypes.c_ubyte * 64)()
     gen = ctypes.c_uint64()
     L.check(lib.vb_ctx_arena_reserve(sc._h, 16 * max(total_recv[rank], 1), handle, ctypes.byref(gen)))
@@ -114,7 +124,7 @@ def p2p_exchange(engine, sh, rank, world, group=None, stats=None):
     tot = (ctypes.c_uint64 * world)(*total_recv)
     L.check(lib.vb_shuffle_export_direct(sh._h, off, tot))        # returns when this rank's stores are done
     dist.barrier(group=group)                                     # everybody's rows have landed
-    rc = (ctypes.c_uint64 * world)(*[allc[src][rank] for src in range(world)])
+    rc = (ctypes.c_uint64 * world)(*recv_counts)
     L.check(lib.vb_shuffle_import_arena(sh._h, rc))
     if stats is not None:
         torch.cuda.synchronize()
