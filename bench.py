@@ -174,6 +174,8 @@ def main():
         torch.cuda.synchronize()
 
     sc = vb.Context(local_rank, profile=True)
+    if world > 1:
+        sc.comm_init(rank, world)      # torch.distributed only bootstraps the NCCL id; the exchange runs inside libvega_b200
     engine = vdist.CudaEngine(sc)
     stream = sc.stream()
     rows = torch.empty((N, 2), dtype=torch.int64, device=dev)       # 16 B/pair resident in HBM

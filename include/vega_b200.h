@@ -58,7 +58,7 @@ enum vb_status {
     VB_ERR_OOM = -3,         /* device or host allocation failed */
     VB_ERR_STATE = -4,       /* wrong phase (map after seal, reduce of a freed shuffle, ...) */
     VB_ERR_UNSUPPORTED = -5, /* dtype/agg combination not implemented */
-    VB_ERR_TOO_LARGE = -6    /* more than 2^32-2 rows in one device-local shuffle */
+    VB_ERR_TOO_LARGE = -6    /* more than 2^32-2 rows in one device-local shuffle / map partition */
 };
 
 enum vb_dtype { VB_U64 = 0, VB_I64 = 1, VB_F64 = 2 };
@@ -113,8 +113,10 @@ VB_API int32_t vb_ctx_set_profile(vb_ctx *ctx, int32_t on);
 VB_API int32_t vb_ctx_device(vb_ctx *ctx);
 /* the cudaStream_t all device work of this context is launched on (for event timing) */
 VB_API void *vb_ctx_stream(vb_ctx *ctx);
-/* bytes currently held by the context's device memory pool / high-water mark */
+/* bytes currently held by the context's (private) device memory pool / high-water mark */
 VB_API int32_t vb_ctx_mem_info(vb_ctx *ctx, uint64_t *reserved, uint64_t *high_water);
+/* give pool memory beyond keep_bytes back to the device (the pool otherwise keeps everything it ever used) */
+VB_API int32_t vb_ctx_trim(vb_ctx *ctx, uint64_t keep_bytes);
 
 /* ---- shuffle lifecycle ---------------------------------------------------------------- */
 VB_API int32_t vb_shuffle_create(vb_ctx *ctx, uint64_t shuffle_id, uint32_t n_map, uint32_t n_reduce,
@@ -164,6 +166,46 @@ VB_API int32_t vb_ctx_peer_open(vb_ctx *ctx, uint32_t peer_rank, const void *han
 VB_API int32_t vb_shuffle_export_counts(vb_shuf *s, uint64_t *counts);
 VB_API int32_t vb_shuffle_export_direct(vb_shuf *s, const uint64_t *dst_row_offset, const uint64_t *dst_total_rows);
 VB_API int32_t vb_shuffle_import_arena(vb_shuf *s, const uint64_t *counts);
+
+/* Free the arenas vb_ctx_arena_reserve outgrew.  Call after the barrier that follows the exchange: by then every
+ * peer has re-opened this rank's current arena (vb_ctx_peer_open closes its mapping of the old one) — freeing an
+ * exported allocation a peer still has mapped is undefined.                                                    */
+VB_API int32_t vb_ctx_arena_release_retired(vb_ctx *ctx);
+
+/* ---- the exchange itself, behind the C ABI (ShuffleFetcher::fetch, src/shuffle/shuffle_fetcher.rs:16-119;
+ *      the tracker hand-shake it replaces: src/map_output_tracker.rs:168-265) ---------------------------------
+ * One process per GPU.  vb_comm_unique_id (rank 0) produces the 128-byte NCCL unique id; the host bootstrap
+ * (vega's tracker channel, torch.distributed, the TCP rendezvous in vega_b200/rendezvous.py, ...) hands it to every rank; vb_ctx_comm_init is
+ * collective over the `world` ranks.  Then, per shuffle, instead of export_prepare / buffers / import:
+ *
+ *     vb_shuffle_map_*(...)  ...  vb_shuffle_exchange(s, VB_XCHG_AUTO);  vb_shuffle_seal(s);
+ *
+ * vb_shuffle_exchange is collective and runs entirely on the library's stream:
+ *   VB_XCHG_NCCL  pack rows by destination rank (combined rows for reduce ops), all-gather the world x world
+ *                 count matrix (one small collective + one D2H), then ONE ncclGroupStart .. ncclSend/ncclRecv
+ *                 .. ncclGroupEnd carrying keys and values of every peer (a single all-to-all-v).
+ *   VB_XCHG_P2P   GROUP/COGROUP: the fused exchange above — the partition kernel stores into the peers'
+ *                 arenas; counts, arena sizes/generations ride one all-gather, IPC handles a second one only
+ *                 when some arena had to grow; a stream-ordered all-gather is the closing barrier.
+ *   VB_XCHG_AUTO  P2P for group ops, NCCL for reduce ops.
+ * NCCL is dlopen'ed (libnccl.so.2) on first use.  vb_ctx_destroy / vb_ctx_comm_destroy are collective when a
+ * communicator exists (peer mappings are closed before the arenas are freed).                                 */
+#define VB_UNIQUE_ID_BYTES 128
+enum vb_xchg { VB_XCHG_AUTO = 0, VB_XCHG_NCCL = 1, VB_XCHG_P2P = 2 };
+typedef struct vb_xstats {
+    uint64_t sent_rows;     /* rows that left this rank (excluding rows it keeps) */
+    uint64_t recv_rows;
+    uint64_t exchanges;
+    double exchange_ms;     /* device time of the exchange (profiling on): NCCL group, or counts+scatter+barrier for P2P */
+    int32_t kind;           /* vb_xchg actually used */
+    int32_t pad;
+} vb_xstats;
+VB_API int32_t vb_comm_unique_id(void *id_out /*VB_UNIQUE_ID_BYTES*/);
+VB_API int32_t vb_ctx_comm_init(vb_ctx *ctx, const void *unique_id, uint32_t rank, uint32_t world);
+VB_API int32_t vb_ctx_comm_destroy(vb_ctx *ctx);
+VB_API int32_t vb_ctx_comm_info(vb_ctx *ctx, uint32_t *rank, uint32_t *world, int32_t *nccl_version);
+VB_API int32_t vb_shuffle_exchange(vb_shuf *s, int32_t mode);
+VB_API int32_t vb_shuffle_exchange_stats(vb_shuf *s, vb_xstats *out);
 
 /* All map outputs are registered: run the reduce side for every partition this rank owns.
  * world == 1: every map_id in [0, n_map) must have been submitted.                          */

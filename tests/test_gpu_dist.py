@@ -1,7 +1,8 @@
 """N>1 path on the GPU: two ranks run the real CudaEngine (export multisplit by destination rank,
-import, seal) and must reproduce the single-process oracle.  With >= 2 GPUs the exchange is NCCL
-over NVLink (one rank per GPU); on a 1-GPU box both ranks share GPU 0 and the all-to-all-v is
-staged through gloo — the library code under test is the same."""
+import, seal) and must reproduce the single-process oracle.  With >= 2 GPUs the exchange is the
+library's own (vb_ctx_comm_init + vb_shuffle_exchange: NCCL grouped send/recv or the fused P2P scatter,
+one rank per GPU); on a 1-GPU box both ranks share GPU 0 (NCCL refuses duplicate devices) and the
+all-to-all-v is staged through gloo — the pack/unpack/seal code under test is the same."""
 import os
 import pickle
 import socket
@@ -50,6 +51,8 @@ def _worker(rank, world, port, agg, M, R, nccl, outdir, p2p=False):
     starts = vb.slice_starts(N_ROWS, M)
     lo, hi = vdist.map_block(rank, world, M)
     sc = vb.Context(dev)
+    if nccl:
+        sc.comm_init(rank, world)      # >= 2 GPUs: the exchange runs inside libvega_b200 (vb_shuffle_exchange)
     eng = vdist.CudaEngine(sc)
     maps = [(m, keys[starts[m]:starts[m + 1]], vals[starts[m]:starts[m + 1]]) for m in range(lo, hi)]
     stats = {}
@@ -97,3 +100,86 @@ def test_two_rank_cuda_shuffle_matches_oracle(agg, M, R, p2p):
         else:
             assert dict(zip(got[0].tolist(), got[1].tolist())) == dict(zip(w["keys"].tolist(), w["combined"].tolist()))
     assert sum(s["sent_rows"] for _, s in per_rank) == sum(s["recv_rows"] for _, s in per_rank) > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-rank join / cogroup (CoGroupedRdd::compute co_grouped_rdd.rs:206-249 + pair_rdd.rs:104-121)
+# ---------------------------------------------------------------------------------------------
+def _join_dataset():
+    rng = np.random.default_rng(77)
+    ka = rng.integers(0, 4000, 60_000).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(3)
+    kb = rng.integers(2000, 7000, 45_000).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(3)
+    va = rng.integers(0, 1 << 50, len(ka)).astype(np.uint64)
+    vb_ = rng.integers(0, 1 << 50, len(kb)).astype(np.uint64)
+    return ka, va, kb, vb_
+
+
+def _join_worker(rank, world, port, Ma, Mb, R, nccl, outdir, p2p):
+    import ctypes
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = rank if nccl else 0
+    torch.cuda.set_device(dev)
+    if nccl:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{dev}"))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vega_b200 as vb
+    from vega_b200 import _lib as L
+    from vega_b200 import dist as vdist
+    ka, va, kb, vb_ = _join_dataset()
+    sc = vb.Context(dev)
+    if nccl:
+        sc.comm_init(rank, world)
+    eng = vdist.CudaEngine(sc)
+    shs = []
+    for keys, vals, M in ((ka, va, Ma), (kb, vb_, Mb)):
+        starts = vb.slice_starts(len(keys), M)
+        lo, hi = vdist.map_block(rank, world, M)
+        maps = [(m, keys[starts[m]:starts[m + 1]], vals[starts[m]:starts[m + 1]]) for m in range(lo, hi)]
+        shs.append(vdist.run_shuffle(eng, maps, M, R, 0, 0, L.VB_AGG_COGROUP, rank, world,
+                                     exchange_device=None if (nccl or p2p) else "cpu", p2p=p2p))
+    sa, sb = shs
+    res, cg = {}, {}
+    for r in range(R):
+        n = ctypes.c_uint64()
+        L.check(sc._lib.vb_join_size(sa._h, sb._h, r, ctypes.byref(n)))
+        k, v, w = (np.empty(n.value, dtype=np.uint64) for _ in range(3))
+        p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+        L.check(sc._lib.vb_join(sa._h, sb._h, r, p(k), p(v), p(w), L.VB_HOST))
+        if r % world != rank:
+            assert n.value == 0
+        res[r] = (k, v, w)
+        cg[r] = ([np.asarray(x) for x in sa.reduce(r)], [np.asarray(x) for x in sb.reduce(r)])   # the cogroup sides
+    with open(os.path.join(outdir, f"j{rank}.pkl"), "wb") as f:
+        pickle.dump((res, cg), f)
+    sa.free(); sb.free()
+    sc.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("Ma,Mb,R,p2p", [(4, 2, 4, False), (3, 5, 6, True), (2, 2, 3, False)])
+def test_two_rank_join_and_cogroup_match_oracle(Ma, Mb, R, p2p):
+    """Full oracle diff of a 2-rank join (every output row, per reduce partition) and of both cogroup sides
+    (ordered value lists per key), over the NCCL / gloo-staged all-to-all-v and the fused P2P exchange."""
+    from oracle import oracle as O
+    world = 2
+    nccl = torch.cuda.device_count() >= 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_join_worker, args=(world, _free_port(), Ma, Mb, R, nccl, d, p2p), nprocs=world, join=True)
+        per_rank = [pickle.load(open(os.path.join(d, f"j{r}.pkl"), "rb")) for r in range(world)]
+    ka, va, kb, vb_ = _join_dataset()
+    want = O.join(ka, va, Ma, kb, vb_, Mb, R)
+    wa, wb = O.shuffle("group", ka, va, Ma, R), O.shuffle("group", kb, vb_, Mb, R)
+    total = 0
+    for r in range(R):
+        got = per_rank[r % world][0][r]
+        assert sorted(zip(*[x.tolist() for x in got])) == sorted(zip(*[x.tolist() for x in want[r]])), f"join partition {r}"
+        total += len(got[0])
+        for side, w in ((0, wa[r]), (1, wb[r])):
+            g = per_rank[r % world][1][r][side]
+            gd = {int(k): g[2][int(g[1][i]):int(g[1][i + 1])].tolist() for i, k in enumerate(g[0])}
+            wd = {int(k): w["vals"][int(w["offsets"][i]):int(w["offsets"][i + 1])].tolist() for i, k in enumerate(w["keys"])}
+            assert gd == wd, f"cogroup side {side} partition {r}"
+    assert total == sum(len(w[0]) for w in want) > 0

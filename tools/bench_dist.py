@@ -35,7 +35,9 @@ dev = f"cuda:{lrank}"
 if world > 1:
     tdist.init_process_group("nccl", device_id=torch.device(dev))
 N, D = int(args.rows), int(args.distinct)
-sc = vb.Context(lrank)
+sc = vb.Context(lrank, profile=True)
+if world > 1:
+    sc.comm_init(rank, world)
 eng = vdist.CudaEngine(sc)
 stream = sc.stream()
 

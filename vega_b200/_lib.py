@@ -16,6 +16,8 @@ VB_AGG_GROUP, VB_AGG_SUM, VB_AGG_MIN, VB_AGG_MAX, VB_AGG_COUNT, VB_AGG_COGROUP, 
 VB_PART_HASH_METRO64, VB_PART_RANGE = 0, 1
 VB_HOST, VB_DEVICE, VB_DEVICE_BORROWED = 0, 1, 2
 VB_GEN_UNIFORM, VB_GEN_ZIPF, VB_GEN_UNIQUE = 0, 1, 2
+VB_XCHG_AUTO, VB_XCHG_NCCL, VB_XCHG_P2P = 0, 1, 2
+VB_UNIQUE_ID_BYTES = 128
 
 KERNEL_CLASSES = ["hash_agg", "dict", "merge", "rp_hist", "rp_scan", "rp_scatter", "misc", "join"]
 
@@ -34,6 +36,11 @@ class vb_stats(ctypes.Structure):
         ("hot_kernel_launches", ctypes.c_uint64), ("hot_kernel_rows", ctypes.c_uint64),
         ("map_ms", ctypes.c_double), ("seal_ms", ctypes.c_double),
     ]
+
+
+class vb_xstats(ctypes.Structure):
+    _fields_ = [("sent_rows", ctypes.c_uint64), ("recv_rows", ctypes.c_uint64), ("exchanges", ctypes.c_uint64),
+                ("exchange_ms", ctypes.c_double), ("kind", ctypes.c_int32), ("pad", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); also the list of symbols include/vega_b200.h declares
@@ -61,6 +68,14 @@ SYMBOLS = {
     "vb_shuffle_export_counts": (_i32, [_vp, _pu64]),
     "vb_shuffle_export_direct": (_i32, [_vp, _pu64, _pu64]),
     "vb_shuffle_import_arena": (_i32, [_vp, _pu64]),
+    "vb_ctx_arena_release_retired": (_i32, [_vp]),
+    "vb_ctx_trim": (_i32, [_vp, _u64]),
+    "vb_comm_unique_id": (_i32, [_vp]),
+    "vb_ctx_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
+    "vb_ctx_comm_destroy": (_i32, [_vp]),
+    "vb_ctx_comm_info": (_i32, [_vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_i32)]),
+    "vb_shuffle_exchange": (_i32, [_vp, _i32]),
+    "vb_shuffle_exchange_stats": (_i32, [_vp, ctypes.POINTER(vb_xstats)]),
     "vb_shuffle_seal": (_i32, [_vp]),
     "vb_shuffle_is_sealed": (_i32, [_vp]),
     "vb_shuffle_reduce_size": (_i32, [_vp, _u32, _pu64, _pu64]),

@@ -182,6 +182,53 @@ VB_D void st_stream_u32(void *p, u32 v)
 {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// ---- mbarrier + bulk async copy (TMA engine, SASS: UBLKCP / SYNCS) ---------------------------------
+// Input tiles are staged global → shared by the copy engine, not through registers: a producer lane
+// posts the expected byte count on an mbarrier and issues one cp.async.bulk per tile; consumers wait
+// on the barrier's phase parity.  (16-byte aligned addresses, sizes multiple of 16.)
+VB_D u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+VB_D void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+VB_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+VB_D void mbar_arrive(u64 *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+VB_D void mbar_arrive_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+VB_D void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global → shared bulk copy, completion counted in bytes on `bar`; L2 policy from createpolicy
+VB_D void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar, u64 pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+// shared → global bulk store (bulk_group completion)
+VB_D void bulk_s2g(void *dst_gmem, const void *src_smem, u32 bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+VB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> VB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> VB_D void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+VB_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+VB_D void named_bar_sync(u32 id, u32 nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+VB_D void named_bar_arrive(u32 id, u32 nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 VB_D u32 lane_id() { return threadIdx.x & 31u; }
 VB_D u32 lanemask_lt()
 {

@@ -76,7 +76,10 @@ struct vb_ctx {
     u64 arena_gen = 0;
     struct Peer { void *base = nullptr; u64 gen = 0; bool self = false; };
     std::map<u32, Peer> peers;
+    std::vector<void *> retired_arenas;   // outgrown arenas some peer may still have mapped: freed by vb_ctx_arena_release_retired
+    struct Comm *comm = nullptr;          // NCCL communicator + exchange scratch (vb_ctx_comm_init)
 };
+static void comm_teardown(vb_ctx *c);
 
 struct DevBuf {   // stream-ordered device allocation, freed on scope exit unless released
     vb_ctx *c = nullptr;
@@ -145,7 +148,16 @@ extern "C" int32_t vb_ctx_create(int32_t device_id, vb_ctx **out)
     CU(cudaGetDeviceProperties(&prop, device_id));
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaDeviceGetDefaultMemPool(&c->pool, device_id));
+    // a private stream-ordered pool: the process-wide default pool (shared with any other cudaMallocAsync
+    // user) is left untouched; ours keeps its memory between shuffles (steady-state steps never call
+    // cudaMalloc) until vb_ctx_trim / vb_ctx_destroy
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device_id;
+    CU(cudaMemPoolCreate(&c->pool, &pp));
     uint64_t thr = ~0ull;
     CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     CU(cudaMallocHost(&c->h_scratch, c->h_scratch_bytes));
@@ -161,10 +173,25 @@ extern "C" int32_t vb_ctx_destroy(vb_ctx *c)
     if (c->zipf_cdf) cudaFreeAsync(c->zipf_cdf, c->stream);
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->peers) if (kv.second.base && !kv.second.self) cudaIpcCloseMemHandle(kv.second.base);
+    // An exported arena must outlive every importer's mapping (cudaFree of a region a peer still has open is
+    // undefined): with a communicator, all ranks close their mappings above, meet at a barrier, then free.
+    comm_teardown(c);
+    for (void *p : c->retired_arenas) cudaFree(p);
     if (c->arena) cudaFree(c->arena);
     cudaFreeHost(c->h_scratch);
     cudaStreamDestroy(c->stream);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     delete c;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_trim(vb_ctx *c, uint64_t keep_bytes)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemPoolTrimTo(c->pool, (size_t)keep_bytes));
     return VB_OK;
 }
 
@@ -250,6 +277,8 @@ struct vb_shuf {
     std::mutex mu;
     std::condition_variable cv;
     bool sealed = false, failed = false, freed = false;
+    bool sealing = false;          // a vb_shuffle_seal is running: a second caller waits for it instead of re-running
+    u32 waiters = 0;               // threads blocked in wait_sealed: vb_shuffle_free drains them before deleting
     // export / import (world > 1)
     bool exported = false, imported = false;
     u64 *exp_keys = nullptr, *exp_vals = nullptr;
@@ -262,6 +291,8 @@ struct vb_shuf {
     bool exp_counted = false;
     const u64 *imp_keys = nullptr, *imp_vals = nullptr;
     u64 imp_n = 0;
+    u64 *imp_own_k = nullptr, *imp_own_v = nullptr;   // receive buffers of vb_shuffle_exchange (freed with the inputs)
+    vb_xstats xst{};
     // gathered input kept alive for the reduce side of group ops
     u64 *gath_keys = nullptr, *gath_vals = nullptr;
     // results
@@ -375,6 +406,7 @@ struct AggInput {
     const u64 *b;
     u64 n;           // rows (IN_TABLE: slots incl. the special one)
     int loc;         // VB_HOST or device
+    u64 items = 0;   // IN_TABLE: upper bound on the occupied slots (n_inserted + 1); 0 = n
 };
 
 template <int IN, int OPK, int TX>
@@ -382,6 +414,23 @@ static int launch_hash_agg_t(vb_shuf *s, int klass, const u64 *a, const u64 *b, 
                              TableCtl *ctl, u64 max_inserts, u32 *slot_out)
 {
     vb_ctx *c = s->ctx;
+    if constexpr (IN != IN_TABLE) {
+        // bulk-staged (copy engine) variant: 16-byte aligned inputs of at least a few tiles per CTA
+        static const bool no_bulk = getenv("VEGA_B200_NO_BULK") != nullptr;
+        const bool aligned = (((uintptr_t)a | (uintptr_t)(b ? b : a)) & 15u) == 0;
+        if (!no_bulk && aligned && n >= (u64)HB_TILE * 64) {
+            auto kb = hash_agg_bulk_kernel<IN, OPK, TX>;
+            constexpr bool has_v = (IN == IN_AOS) || (OPK != OPK_COUNT && OPK != OPK_DICT);
+            const size_t smem = hb_smem_bytes(has_v);
+            if (c->occ_cache.find((const void *)kb) == c->occ_cache.end())
+                CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = occupancy(c, kb, HB_THREADS, smem);
+            u64 grid = std::min<u64>(n / HB_TILE, (u64)c->sm_count * occ);
+            KLaunch kl(s, klass, n);
+            kb<<<(unsigned)grid, HB_THREADS, smem, c->stream>>>(a, b, n, table_at(tab, log_cap), ctl, max_inserts, slot_out);
+            return kl.done("hash_agg_bulk_kernel");
+        }
+    }
     auto kern = hash_agg_kernel<IN, OPK, TX>;
     int occ = occupancy(c, kern, HA_THREADS, 0);
     u64 tiles = (n + HA_TILE - 1) / HA_TILE;
@@ -526,16 +575,17 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
                        void **out_tab, u32 *out_log_cap, u64 *out_inserted, u32 *slot_out)
 {
     vb_ctx *c = s->ctx;
-    u64 total = 0;
+    u64 total = 0;          // items that can each bring a new key (table inputs: occupied slots, not capacity)
     bool any_host = false;
     u64 max_host = 0;
     for (auto &in : inputs) {
-        total += in.n;
+        total += in.items ? std::min(in.items, in.n) : in.n;
         if (in.loc == VB_HOST) { any_host = true; max_host = std::max(max_host, in.n); }
     }
     if (slot_out && any_host) return set_err(VB_ERR_INVALID, "build_table: dictionary inputs must be on the device");
-    u32 max_log = std::max<u32>(4, ceil_log2_u64(2 * std::max<u64>(total, 1)));
-    if (max_log > MAX_LOG_CAP) return set_err(VB_ERR_TOO_LARGE, "shuffle %llu: %llu rows exceed the device-local limit", (unsigned long long)s->id, (unsigned long long)total);
+    // capacity never needs to exceed 2x the items; slot indices are 32-bit, so 2^31 slots is the ceiling — an input
+    // with more than ~1.3e9 distinct keys fails with "overflow at maximum capacity", fewer distinct keys fit whatever the row count
+    const u32 max_log = std::min<u32>(MAX_LOG_CAP, std::max<u32>(4, ceil_log2_u64(2 * std::max<u64>(total, 1))));
     bool estimated = false;
     if (!hint_distinct && total > (1ull << 20)) { TRY(estimate_distinct(s, inputs, total, &hint_distinct)); estimated = true; }
     u32 log_cap = choose_log_cap(total, hint_distinct, estimated, max_log);
@@ -1251,7 +1301,7 @@ static int merge_map_tables(vb_shuf *s, void **tab, u32 *log_cap, u64 *n_ins)
     u64 max_ins = 0;
     for (auto &t : ts) {
         const Table mt = table_at(t.tab, t.log_cap);
-        in.push_back(AggInput{IN_TABLE, mt.keys, mt.accs, (1ull << t.log_cap) + 1, VB_DEVICE});
+        in.push_back(AggInput{IN_TABLE, mt.keys, mt.accs, (1ull << t.log_cap) + 1, VB_DEVICE, t.ins + 1});
         max_ins = std::max(max_ins, t.ins);
     }
     TRY(build_table(s, K_MERGE, in, merge_opk(s), TX_NONE, std::max<u64>(max_ins, s->hint), tab, log_cap, n_ins, nullptr));
@@ -1374,19 +1424,19 @@ static void release_inputs(vb_shuf *s)
     dev_free(s->ctx, s->exp_hist);
     s->exp_keys = s->exp_vals = nullptr;
     s->exp_hist = nullptr;
+    dev_free(s->ctx, s->imp_own_k);
+    dev_free(s->ctx, s->imp_own_v);
+    s->imp_own_k = s->imp_own_v = nullptr;
 }
 
-extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
+// Finish the local map side and pack rows by destination rank (caller holds c->mu).
+static int export_prepare_locked(vb_shuf *s, uint64_t *counts)
 {
-    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
-    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_export_prepare needs vb_shuffle_set_dist(world > 1)");
     vb_ctx *c = s->ctx;
     {
         std::lock_guard<std::mutex> g(s->mu);
         if (s->sealed || s->exported || s->freed) return set_err(VB_ERR_STATE, "export after seal/export");
     }
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU(cudaSetDevice(c->device));
     std::vector<u64> off;
     if (is_reduce_op(s->agg)) {
         void *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
@@ -1418,23 +1468,33 @@ extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
         }
     }
     for (u32 r = 0; r < s->world; ++r) counts[r] = off[r + 1] - off[r];
-    CU(cudaStreamSynchronize(c->stream));
     std::lock_guard<std::mutex> g(s->mu);
     s->exported = true;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_export_prepare(vb_shuf *s, uint64_t *counts)
+{
+    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_export_prepare needs vb_shuffle_set_dist(world > 1)");
+    vb_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(export_prepare_locked(s, counts));
+    CU(cudaStreamSynchronize(c->stream));
     return VB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // P2P exchange: rows go straight from the partition kernel into the peers' HBM over NVLink
 // ---------------------------------------------------------------------------------------------
-extern "C" int32_t vb_ctx_arena_reserve(vb_ctx *c, uint64_t bytes, void *handle_out, uint64_t *generation)
+static int arena_reserve_locked(vb_ctx *c, uint64_t bytes, void *handle_out, uint64_t *generation)
 {
-    if (!c || !handle_out || !generation) return set_err(VB_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU(cudaSetDevice(c->device));
     if (bytes > c->arena_bytes || !c->arena) {
         CU(cudaStreamSynchronize(c->stream));
-        if (c->arena) CU(cudaFree(c->arena));
+        // peers may still have the old allocation mapped (they close it in vb_ctx_peer_open when they see the new
+        // generation): keep it until vb_ctx_arena_release_retired, which the caller invokes after a barrier
+        if (c->arena) c->retired_arenas.push_back(c->arena);
         c->arena = nullptr;
         size_t want = std::max<size_t>((size_t)bytes + bytes / 4, (size_t)64 << 20);
         want = (want + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
@@ -1450,11 +1510,29 @@ extern "C" int32_t vb_ctx_arena_reserve(vb_ctx *c, uint64_t bytes, void *handle_
     return VB_OK;
 }
 
-extern "C" int32_t vb_ctx_peer_open(vb_ctx *c, uint32_t peer_rank, const void *handle, uint64_t generation, int32_t is_self)
+extern "C" int32_t vb_ctx_arena_reserve(vb_ctx *c, uint64_t bytes, void *handle_out, uint64_t *generation)
 {
-    if (!c || (!handle && !is_self)) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (!c || !handle_out || !generation) return set_err(VB_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    return arena_reserve_locked(c, bytes, handle_out, generation);
+}
+
+// Free the arenas outgrown by vb_ctx_arena_reserve.  Contract: every peer has called vb_ctx_peer_open with this
+// rank's current generation (which closes its mapping of the old one) — i.e. call it after the barrier that
+// follows the exchange.
+extern "C" int32_t vb_ctx_arena_release_retired(vb_ctx *c)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    for (void *p : c->retired_arenas) CU(cudaFree(p));
+    c->retired_arenas.clear();
+    return VB_OK;
+}
+
+static int peer_open_locked(vb_ctx *c, uint32_t peer_rank, const void *handle, uint64_t generation, int32_t is_self)
+{
     auto &p = c->peers[peer_rank];
     if (is_self) { p.base = c->arena; p.gen = c->arena_gen; p.self = true; return VB_OK; }
     if (p.base && p.gen == generation && !p.self) return VB_OK;
@@ -1467,21 +1545,25 @@ extern "C" int32_t vb_ctx_peer_open(vb_ctx *c, uint32_t peer_rank, const void *h
     return VB_OK;
 }
 
+extern "C" int32_t vb_ctx_peer_open(vb_ctx *c, uint32_t peer_rank, const void *handle, uint64_t generation, int32_t is_self)
+{
+    if (!c || (!handle && !is_self)) return set_err(VB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return peer_open_locked(c, peer_rank, handle, generation, is_self);
+}
+
 // Histogram of this rank's rows by destination rank (no data movement yet); keeps the scanned
 // per-part histogram for vb_shuffle_export_direct.  group ops only (reduce ops exchange a few MB of
 // combined rows: vb_shuffle_export_prepare + one all-to-all-v is the right tool there).
-extern "C" int32_t vb_shuffle_export_counts(vb_shuf *s, uint64_t *counts)
+static int export_counts_locked(vb_shuf *s, uint64_t *counts)
 {
-    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
-    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_export_counts needs vb_shuffle_set_dist(world > 1)");
     if (!is_group_op(s->agg)) return set_err(VB_ERR_UNSUPPORTED, "the fused P2P export is for GROUP/COGROUP shuffles");
     vb_ctx *c = s->ctx;
     {
         std::lock_guard<std::mutex> g(s->mu);
         if (s->sealed || s->exported || s->exp_counted || s->freed) return set_err(VB_ERR_STATE, "export after seal/export");
     }
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU(cudaSetDevice(c->device));
     Gathered g;
     TRY(gather_maps(s, &g));
     s->exp_rows = g.rows; s->exp_k = g.keys; s->exp_v = g.vals; s->exp_n = g.n;
@@ -1504,17 +1586,23 @@ extern "C" int32_t vb_shuffle_export_counts(vb_shuf *s, uint64_t *counts)
     return VB_OK;
 }
 
+extern "C" int32_t vb_shuffle_export_counts(vb_shuf *s, uint64_t *counts)
+{
+    if (!s || !counts) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_export_counts needs vb_shuffle_set_dist(world > 1)");
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    return export_counts_locked(s, counts);
+}
+
 // The scatter: every row is stored into the arena of the rank that owns its reduce partition.
 // dst_row_offset[d]: first row of my block inside rank d's arena; dst_total_rows[d]: rows rank d receives in total
 // (its arena holds keys[total] then vals[total]).  Returns after the stores are complete on this GPU; the
 // host then barriers the ranks before anyone reads its arena.
-extern "C" int32_t vb_shuffle_export_direct(vb_shuf *s, const uint64_t *dst_row_offset, const uint64_t *dst_total_rows)
+static int export_direct_locked(vb_shuf *s, const uint64_t *dst_row_offset, const uint64_t *dst_total_rows, bool sync)
 {
-    if (!s || !dst_row_offset || !dst_total_rows) return set_err(VB_ERR_INVALID, "NULL argument");
     if (!s->exp_counted || s->exported) return set_err(VB_ERR_STATE, "vb_shuffle_export_direct needs vb_shuffle_export_counts first");
     vb_ctx *c = s->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU(cudaSetDevice(c->device));
     const u32 W = s->world;
     if (s->exp_n) {
         std::vector<u64 *> hk(W), hv(W);
@@ -1553,13 +1641,21 @@ extern "C" int32_t vb_shuffle_export_direct(vb_shuf *s, const uint64_t *dst_row_
         void *args[] = {&ld, &dg, &n, &rpp, &ch, &np, &nullk, &nullv, &rd};
         CU(cudaLaunchKernel(sk, dim3(np), dim3(RPS_THREADS), args, smem, c->stream));
         TRY(kl.done("rp_scatter_kernel<REMOTE>"));
-        CU(cudaStreamSynchronize(c->stream));
+        if (sync) CU(cudaStreamSynchronize(c->stream));
     }
     dev_free(c, s->exp_hist);
     s->exp_hist = nullptr;
     std::lock_guard<std::mutex> g(s->mu);
     s->exported = true;
     return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_export_direct(vb_shuf *s, const uint64_t *dst_row_offset, const uint64_t *dst_total_rows)
+{
+    if (!s || !dst_row_offset || !dst_total_rows) return set_err(VB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    return export_direct_locked(s, dst_row_offset, dst_total_rows, true);
 }
 
 // The rows of every source rank are already in this context's arena (keys[total] then vals[total],
@@ -1603,6 +1699,322 @@ extern "C" int32_t vb_shuffle_import(vb_shuf *s, const void *keys_dev, const voi
     return VB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The exchange behind the C ABI (ShuffleFetcher::fetch, src/shuffle/shuffle_fetcher.rs:16-119):
+// one NCCL communicator per context, counts + rows exchanged on the library's own stream.
+// NCCL is loaded with dlopen on first use, so single-GPU users carry no dependency on it.
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static int nccl_load()
+{
+    std::lock_guard<std::mutex> g(g_nccl_mu);
+    if (g_nccl.h) return VB_OK;
+    const char *names[] = {getenv("VEGA_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        if (!nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return set_err(VB_ERR_UNSUPPORTED, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+#define LD(f)                                                                                      \
+    do {                                                                                           \
+        *(void **)(&g_nccl.f) = dlsym(h, "nccl" #f);                                               \
+        if (!g_nccl.f) return set_err(VB_ERR_UNSUPPORTED, "libnccl lacks nccl" #f);                \
+    } while (0)
+    LD(GetUniqueId); LD(CommInitRank); LD(CommDestroy); LD(GroupStart); LD(GroupEnd); LD(Send); LD(Recv); LD(AllGather);
+    LD(GetErrorString); LD(GetVersion);
+#undef LD
+    g_nccl.h = h;
+    return VB_OK;
+}
+
+#define NC(expr)                                                                                             \
+    do {                                                                                                     \
+        ncclResult_t r_ = (expr);                                                                            \
+        if (r_ != ncclSuccess) return set_err(VB_ERR_CUDA, "%s:%d %s: NCCL %s", __FILE__, __LINE__, #expr,    \
+                                              g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "error");   \
+    } while (0)
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    u32 rank = 0, world = 1;
+    u64 *d_send = nullptr;     // [world + 2]: counts to every destination, arena bytes, arena generation
+    u64 *d_recv = nullptr;     // [world][world + 2]
+    unsigned char *d_hs = nullptr, *d_hr = nullptr;   // IPC handle + generation: 80 bytes, [world] x 80
+    std::vector<u64> peer_arena_bytes, peer_gen_seen;
+    bool handles_valid = false;
+};
+constexpr u32 COMM_MAX_WORLD = 64;
+constexpr size_t COMM_HOST_OFF = 256 << 10;   // staging region inside vb_ctx::h_scratch
+
+static void comm_teardown(vb_ctx *c)
+{
+    Comm *m = c->comm;
+    if (!m) return;
+    // every rank has closed its peer mappings before this point; the all-gather is the barrier that lets the
+    // owners free the exported arenas afterwards
+    if (m->comm && g_nccl.AllGather && m->d_send && m->d_recv) {
+        if (g_nccl.AllGather(m->d_send, m->d_recv, 1, ncclUint64, m->comm, c->stream) == ncclSuccess) cudaStreamSynchronize(c->stream);
+    }
+    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    cudaFree(m->d_send); cudaFree(m->d_recv); cudaFree(m->d_hs); cudaFree(m->d_hr);
+    cudaGetLastError();
+    delete m;
+    c->comm = nullptr;
+}
+
+extern "C" int32_t vb_comm_unique_id(void *id_out)
+{
+    if (!id_out) return set_err(VB_ERR_INVALID, "id_out is NULL");
+    TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == VB_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_comm_init(vb_ctx *c, const void *unique_id, uint32_t rank, uint32_t world)
+{
+    if (!c || !unique_id) return set_err(VB_ERR_INVALID, "NULL argument");
+    if (world < 1 || rank >= world || world > COMM_MAX_WORLD) return set_err(VB_ERR_INVALID, "bad rank/world (world <= %u)", COMM_MAX_WORLD);
+    TRY(nccl_load());
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (c->comm) return set_err(VB_ERR_STATE, "context already has a communicator");
+    Comm *m = new Comm();
+    m->rank = rank; m->world = world;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&m->comm, (int)world, id, (int)rank);
+    if (r != ncclSuccess) { delete m; return set_err(VB_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    c->comm = m;
+    CU(cudaMalloc((void **)&m->d_send, (world + 2) * 8));
+    CU(cudaMalloc((void **)&m->d_recv, (size_t)world * (world + 2) * 8));
+    CU(cudaMalloc((void **)&m->d_hs, 80));
+    CU(cudaMalloc((void **)&m->d_hr, (size_t)world * 80));
+    CU(cudaMemset(m->d_send, 0, (world + 2) * 8));
+    m->peer_arena_bytes.assign(world, 0);
+    m->peer_gen_seen.assign(world, 0);
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_comm_destroy(vb_ctx *c)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &kv : c->peers) if (kv.second.base && !kv.second.self) { cudaIpcCloseMemHandle(kv.second.base); kv.second.base = nullptr; }
+    c->peers.clear();
+    comm_teardown(c);
+    return VB_OK;
+}
+
+extern "C" int32_t vb_ctx_comm_info(vb_ctx *c, uint32_t *rank, uint32_t *world, int32_t *nccl_version)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    if (!c->comm) return set_err(VB_ERR_STATE, "no communicator (vb_ctx_comm_init)");
+    if (rank) *rank = c->comm->rank;
+    if (world) *world = c->comm->world;
+    if (nccl_version) { int v = 0; g_nccl.GetVersion(&v); *nccl_version = v; }
+    return VB_OK;
+}
+
+// All-gather of (counts[world], my arena bytes, my arena generation) — ONE small collective + one D2H —
+// into the pinned staging area.  Returns the matrix as host rows of (world + 2) u64.
+static int comm_gather_counts(vb_ctx *c, const u64 *counts, const u64 **matrix)
+{
+    Comm *m = c->comm;
+    const u32 W = m->world;
+    u64 *h = (u64 *)((char *)c->h_scratch + COMM_HOST_OFF);
+    u64 *hs = h + (size_t)W * (W + 2);
+    for (u32 d = 0; d < W; ++d) hs[d] = counts[d];
+    hs[W] = c->arena_bytes;
+    hs[W + 1] = c->arena_gen;
+    CU(cudaMemcpyAsync(m->d_send, hs, (W + 2) * 8, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(m->d_send, m->d_recv, W + 2, ncclUint64, m->comm, c->stream));
+    CU(cudaMemcpyAsync(h, m->d_recv, (size_t)W * (W + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *matrix = h;
+    return VB_OK;
+}
+
+// reduce ops and non-P2P group ops: pack by destination, then ONE grouped send/recv carrying both columns
+static int exchange_nccl_locked(vb_shuf *s)
+{
+    vb_ctx *c = s->ctx;
+    Comm *m = c->comm;
+    const u32 W = m->world, me = m->rank;
+    std::vector<u64> counts(W, 0);
+    TRY(export_prepare_locked(s, counts.data()));
+    const u64 *mat = nullptr;
+    TRY(comm_gather_counts(c, counts.data(), &mat));
+    std::vector<u64> rcnt(W), soff(W + 1, 0), roff(W + 1, 0);
+    for (u32 p = 0; p < W; ++p) {
+        rcnt[p] = mat[(size_t)p * (W + 2) + me];
+        soff[p + 1] = soff[p] + counts[p];
+        roff[p + 1] = roff[p] + rcnt[p];
+    }
+    const u64 n_recv = roff[W];
+    if (n_recv >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "rank %u would receive %llu rows", me, (unsigned long long)n_recv);
+    DevBuf rk(c), rv(c);
+    TRY(rk.alloc(std::max<u64>(n_recv, 1) * 8));
+    TRY(rv.alloc(std::max<u64>(n_recv, 1) * 8));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    NC(g_nccl.GroupStart());
+    for (u32 p = 0; p < W; ++p) {
+        if (counts[p]) {
+            NC(g_nccl.Send(s->exp_keys + soff[p], counts[p], ncclUint64, (int)p, m->comm, c->stream));
+            NC(g_nccl.Send(s->exp_vals + soff[p], counts[p], ncclUint64, (int)p, m->comm, c->stream));
+        }
+        if (rcnt[p]) {
+            NC(g_nccl.Recv(rk.as<u64>() + roff[p], rcnt[p], ncclUint64, (int)p, m->comm, c->stream));
+            NC(g_nccl.Recv(rv.as<u64>() + roff[p], rcnt[p], ncclUint64, (int)p, m->comm, c->stream));
+        }
+    }
+    NC(g_nccl.GroupEnd());
+    if (e0) {
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        s->xst.exchange_ms += ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    s->xst.sent_rows += soff[W] - counts[me];
+    s->xst.recv_rows += n_recv - rcnt[me];
+    s->xst.exchanges += 1;
+    s->xst.kind = VB_XCHG_NCCL;
+    s->imp_own_k = (u64 *)rk.release();
+    s->imp_own_v = (u64 *)rv.release();
+    s->imp_keys = s->imp_own_k; s->imp_vals = s->imp_own_v; s->imp_n = n_recv;
+    s->imported = true;
+    return VB_OK;
+}
+
+// group ops: the destination-rank partition kernel stores straight into the owners' arenas (peer memory)
+static int exchange_p2p_locked(vb_shuf *s)
+{
+    vb_ctx *c = s->ctx;
+    Comm *m = c->comm;
+    const u32 W = m->world, me = m->rank;
+    std::vector<u64> counts(W, 0);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    TRY(export_counts_locked(s, counts.data()));
+    const u64 *mat = nullptr;
+    TRY(comm_gather_counts(c, counts.data(), &mat));
+    // arena layout (source-rank major = map-id order) from the count matrix
+    std::vector<u64> total(W, 0), my_off(W, 0), rcnt(W);
+    for (u32 dst = 0; dst < W; ++dst)
+        for (u32 src = 0; src < W; ++src) {
+            const u64 x = mat[(size_t)src * (W + 2) + dst];
+            if (src < me) my_off[dst] += x;
+            total[dst] += x;
+        }
+    for (u32 src = 0; src < W; ++src) rcnt[src] = mat[(size_t)src * (W + 2) + me];
+    // who must (re)grow its arena is a pure function of the gathered matrix: handles are re-exchanged only then
+    bool any_regrow = !m->handles_valid;
+    for (u32 p = 0; p < W; ++p) {
+        const u64 need = 16 * std::max<u64>(total[p], 1), have = mat[(size_t)p * (W + 2) + W], gen = mat[(size_t)p * (W + 2) + W + 1];
+        if (need > have || gen == 0 || gen != m->peer_gen_seen[p]) any_regrow = true;
+    }
+    unsigned char hbuf[80];
+    u64 gen = 0;
+    TRY(arena_reserve_locked(c, 16 * std::max<u64>(total[me], 1), hbuf, &gen));
+    if (any_regrow) {
+        memcpy(hbuf + 64, &gen, 8);
+        memset(hbuf + 72, 0, 8);
+        unsigned char *hh = (unsigned char *)c->h_scratch + COMM_HOST_OFF + 128 * 1024;
+        memcpy(hh, hbuf, 80);
+        CU(cudaMemcpyAsync(m->d_hs, hh, 80, cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllGather(m->d_hs, m->d_hr, 80, ncclUint8, m->comm, c->stream));
+        CU(cudaMemcpyAsync(hh + 128, m->d_hr, (size_t)W * 80, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (u32 p = 0; p < W; ++p) {
+            u64 pg;
+            memcpy(&pg, hh + 128 + (size_t)p * 80 + 64, 8);
+            TRY(peer_open_locked(c, p, hh + 128 + (size_t)p * 80, pg, p == me));
+            m->peer_gen_seen[p] = pg;
+        }
+        m->handles_valid = true;
+    }
+    TRY(export_direct_locked(s, my_off.data(), total.data(), false));
+    // stream-ordered barrier: every rank's stores precede its part of this collective, which precedes my reads
+    NC(g_nccl.AllGather(m->d_send, m->d_recv, 1, ncclUint64, m->comm, c->stream));
+    if (any_regrow) {       // every peer has re-opened: outgrown arenas can go
+        CU(cudaStreamSynchronize(c->stream));
+        for (void *p : c->retired_arenas) CU(cudaFree(p));
+        c->retired_arenas.clear();
+    }
+    u64 n = 0;
+    for (u32 r = 0; r < W; ++r) n += rcnt[r];
+    if (n >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "import of %llu rows", (unsigned long long)n);
+    s->imp_keys = (const u64 *)c->arena;
+    s->imp_vals = s->imp_keys + n;
+    s->imp_n = n;
+    s->imported = true;
+    if (e0) {
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        s->xst.exchange_ms += ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    u64 sent = 0;
+    for (u32 p = 0; p < W; ++p) if (p != me) sent += counts[p];
+    s->xst.sent_rows += sent;
+    s->xst.recv_rows += n - rcnt[me];
+    s->xst.exchanges += 1;
+    s->xst.kind = VB_XCHG_P2P;
+    return VB_OK;
+}
+
+extern "C" int32_t vb_shuffle_exchange(vb_shuf *s, int32_t mode)
+{
+    if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
+    vb_ctx *c = s->ctx;
+    if (s->world < 2) return set_err(VB_ERR_STATE, "vb_shuffle_exchange needs vb_shuffle_set_dist(world > 1)");
+    if (!c->comm) return set_err(VB_ERR_STATE, "vb_shuffle_exchange needs vb_ctx_comm_init");
+    if (c->comm->world != s->world || c->comm->rank != s->rank) return set_err(VB_ERR_INVALID, "shuffle rank/world differ from the communicator's");
+    if (mode < VB_XCHG_AUTO || mode > VB_XCHG_P2P) return set_err(VB_ERR_INVALID, "bad exchange mode");
+    if (mode == VB_XCHG_AUTO) mode = is_group_op(s->agg) ? VB_XCHG_P2P : VB_XCHG_NCCL;
+    if (mode == VB_XCHG_P2P && !is_group_op(s->agg)) return set_err(VB_ERR_UNSUPPORTED, "the fused P2P exchange is for GROUP/COGROUP shuffles");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return mode == VB_XCHG_P2P ? exchange_p2p_locked(s) : exchange_nccl_locked(s);
+}
+
+extern "C" int32_t vb_shuffle_exchange_stats(vb_shuf *s, vb_xstats *out)
+{
+    if (!s || !out) return set_err(VB_ERR_INVALID, "NULL argument");
+    *out = s->xst;
+    return VB_OK;
+}
+
 extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
 {
     if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
@@ -1611,6 +2023,19 @@ extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
         std::lock_guard<std::mutex> g(s->mu);
         if (s->freed) return set_err(VB_ERR_STATE, "seal of a freed shuffle");
         if (s->sealed) return VB_OK;
+    }
+    {
+        std::unique_lock<std::mutex> g(s->mu);
+        if (s->sealing) {           // concurrent seal: wait for the one in flight
+            ++s->waiters;
+            s->cv.wait(g, [&] { return !s->sealing || s->freed; });
+            --s->waiters;
+            s->cv.notify_all();
+            if (s->sealed) return VB_OK;
+            return set_err(VB_ERR_STATE, "shuffle %llu: the concurrent seal failed or the shuffle was freed", (unsigned long long)s->id);
+        }
+        if (s->sealed) return VB_OK;
+        s->sealing = true;
     }
     int rc = VB_OK;
     {
@@ -1657,6 +2082,7 @@ extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
     }
     std::lock_guard<std::mutex> g(s->mu);
     if (rc == VB_OK) s->sealed = true; else s->failed = true;
+    s->sealing = false;
     s->cv.notify_all();
     return rc;
 }
@@ -1666,8 +2092,14 @@ extern "C" int32_t vb_shuffle_is_sealed(vb_shuf *s) { return s && s->sealed ? 1 
 static int wait_sealed(vb_shuf *s)
 {
     std::unique_lock<std::mutex> g(s->mu);
+    ++s->waiters;
     s->cv.wait(g, [&] { return s->sealed || s->failed || s->freed; });
-    if (!s->sealed) return set_err(VB_ERR_STATE, "shuffle %llu failed or was freed before it was sealed", (unsigned long long)s->id);
+    --s->waiters;
+    const bool ok = s->sealed && !s->freed;
+    const unsigned long long id = s->id;
+    s->cv.notify_all();            // vb_shuffle_free waits for waiters == 0 (s may be deleted once g is released)
+    g.unlock();
+    if (!ok) return set_err(VB_ERR_STATE, "shuffle %llu failed or was freed before it was sealed", id);
     return VB_OK;
 }
 
@@ -1948,9 +2380,10 @@ extern "C" int32_t vb_shuffle_free(vb_shuf *s)
     if (!s) return VB_OK;
     vb_ctx *c = s->ctx;
     {
-        std::lock_guard<std::mutex> g(s->mu);
+        std::unique_lock<std::mutex> g(s->mu);
         s->freed = true;
         s->cv.notify_all();
+        s->cv.wait(g, [&] { return s->waiters == 0 && !s->sealing; });   // blocked reduce/join/seal callers leave first
     }
     {
         std::lock_guard<std::mutex> lk(c->mu);

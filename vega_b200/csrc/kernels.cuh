@@ -170,6 +170,83 @@ VB_D int cache_combine(u64 *hc_keys, u64 *hc_acc, u64 h, u64 key, u64 v)
     return 0;
 }
 
+// The per-tile work shared by the register-staged and the bulk-staged kernels: thread-private rows
+// k/v/ok (HA_ROWS of them, row j of the thread is input row row0 + j * HA_THREADS) → special key,
+// hot-key cache, then lockstep probe rounds with one RED per resolved row.
+template <int OPK, int TX, bool CACHE, int ROWS>
+VB_D void ha_process_rows(const Table &t, TableCtl *ctl, u64 (&k)[ROWS], u64 (&v)[ROWS], bool (&ok)[ROWS], u64 row0,
+                          u32 *__restrict__ slot_out, u64 *hc_keys, u64 *hc_acc, bool use_cache, u32 &my_inserts, u32 &my_hits)
+{
+    const u64 cap = 1ull << t.log_cap;
+    const u32 hshift = 64 - (t.log_cap - 2);
+    u64 h[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        h[j] = slot_hash(k[j]);
+        if (TX != TX_NONE) v[j] = tx_fwd(v[j], TX);
+        if (ok[j] && k[j] == EMPTY_KEY) {           // a real key equal to the empty marker: special slot
+            t.keys[cap] = 1ull;
+            op_red<OPK>(&t.accs[cap], v[j]);
+            if (OPK == OPK_DICT) st_stream_u32(slot_out + row0 + (u64)j * HA_THREADS, (u32)cap);
+            ok[j] = false;
+        }
+    }
+    if (CACHE && use_cache) {
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            if (!ok[j]) continue;
+            const int c = cache_combine<OPK>(hc_keys, hc_acc, h[j], k[j], v[j]);
+            if (c) { ok[j] = false; my_hits += (c == 1); }
+        }
+    }
+    // Probe rounds run in lockstep over the ROWS rows of a thread: every round first consumes the
+    // buckets loaded by the previous one, then issues the next probes of all unresolved rows together,
+    // so a tile costs max-over-rows (not sum-over-rows) dependent L2 latencies.
+    Bucket4 bk[ROWS];
+    u64 bidx[ROWS];
+    const u64 nb_mask = (1ull << (t.log_cap - 2)) - 1;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        bidx[j] = h[j] >> hshift;
+        if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
+    }
+    bool pending = true;
+#pragma unroll 1
+    for (u32 probe = 0; pending && probe < HA_MAX_PROBE; ++probe) {
+        pending = false;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            if (!ok[j]) continue;
+            int hit = bucket_find(bk[j], k[j]);
+            if (hit < 0) {
+                const int e = bucket_find(bk[j], EMPTY_KEY);
+                if (e < 0) {
+                    bidx[j] = (bidx[j] + 1) & nb_mask;                    // bucket full: next bucket
+                } else {
+                    const u64 old = atomicCAS((unsigned long long *)&t.keys[4 * bidx[j] + e], (unsigned long long)EMPTY_KEY,
+                                              (unsigned long long)k[j]);
+                    if (old == EMPTY_KEY) { ++my_inserts; hit = e; }
+                    else if (old == k[j]) hit = e;                        // else: lost the slot, re-read this bucket
+                }
+            }
+            if (hit >= 0) {
+                const u64 sl = 4 * bidx[j] + (u64)hit;
+                op_red<OPK>(&t.accs[sl], v[j]);
+                if (OPK == OPK_DICT) st_stream_u32(slot_out + row0 + (u64)j * HA_THREADS, (u32)sl);
+                ok[j] = false;
+            } else {
+                pending = true;
+            }
+        }
+        if (pending) {
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j)
+                if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
+        }
+    }
+    if (pending) atomicExch(&ctl->abort, 1u);   // probe chain longer than HA_MAX_PROBE buckets
+}
+
 // One pass over n rows.  IN_AOS: a = rows (16 B each).  IN_SOA: a = keys, b = vals (b may be
 // NULL for COUNT/DICT).  IN_TABLE: a/b = keys/accs of a source table of n-1 slots + the special slot.
 // TX: order-preserving value transform applied on load (MIN/MAX over i64/f64).
@@ -191,8 +268,6 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Tab
         for (u32 i = tid; i < HC_SLOTS; i += HA_THREADS) { hc_keys[i] = EMPTY_KEY; hc_acc[i] = op_identity(OPK); }
     __syncthreads();
     const u64 pol = policy_evict_first();
-    const u64 cap = 1ull << t.log_cap;
-    const u32 hshift = 64 - (t.log_cap - 2);
     const u64 n_tiles = (n + HA_TILE - 1) / HA_TILE;
     u32 my_inserts = 0, my_hits = 0;
     u32 iter = 0;
@@ -221,72 +296,7 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Tab
                 }
             }
         }
-        u64 h[HA_ROWS];
-#pragma unroll
-        for (int j = 0; j < HA_ROWS; ++j) {
-            h[j] = slot_hash(k[j]);
-            if (TX != TX_NONE) v[j] = tx_fwd(v[j], TX);
-            if (ok[j] && k[j] == EMPTY_KEY) {           // a real key equal to the empty marker: special slot
-                t.keys[cap] = 1ull;
-                op_red<OPK>(&t.accs[cap], v[j]);
-                if (OPK == OPK_DICT) st_stream_u32(slot_out + base + (u64)j * HA_THREADS + tid, (u32)cap);
-                ok[j] = false;
-            }
-        }
-        if (CACHE && use_cache) {
-#pragma unroll
-            for (int j = 0; j < HA_ROWS; ++j) {
-                if (!ok[j]) continue;
-                const int c = cache_combine<OPK>(hc_keys, hc_acc, h[j], k[j], v[j]);
-                if (c) { ok[j] = false; my_hits += (c == 1); }
-            }
-        }
-        // Probe rounds run in lockstep over the HA_ROWS rows of a thread: every round first consumes the
-        // buckets loaded by the previous one, then issues the next probes of all unresolved rows together,
-        // so a tile costs max-over-rows (not sum-over-rows) dependent L2 latencies.
-        Bucket4 bk[HA_ROWS];
-        u64 bidx[HA_ROWS];
-        const u64 nb_mask = (1ull << (t.log_cap - 2)) - 1;
-#pragma unroll
-        for (int j = 0; j < HA_ROWS; ++j) {
-            bidx[j] = h[j] >> hshift;
-            if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
-        }
-        bool pending = true;
-#pragma unroll 1
-        for (u32 probe = 0; pending && probe < HA_MAX_PROBE; ++probe) {
-            pending = false;
-#pragma unroll
-            for (int j = 0; j < HA_ROWS; ++j) {
-                if (!ok[j]) continue;
-                int hit = bucket_find(bk[j], k[j]);
-                if (hit < 0) {
-                    const int e = bucket_find(bk[j], EMPTY_KEY);
-                    if (e < 0) {
-                        bidx[j] = (bidx[j] + 1) & nb_mask;                    // bucket full: next bucket
-                    } else {
-                        const u64 old = atomicCAS((unsigned long long *)&t.keys[4 * bidx[j] + e], (unsigned long long)EMPTY_KEY,
-                                                  (unsigned long long)k[j]);
-                        if (old == EMPTY_KEY) { ++my_inserts; hit = e; }
-                        else if (old == k[j]) hit = e;                        // else: lost the slot, re-read this bucket
-                    }
-                }
-                if (hit >= 0) {
-                    const u64 sl = 4 * bidx[j] + (u64)hit;
-                    op_red<OPK>(&t.accs[sl], v[j]);
-                    if (OPK == OPK_DICT) st_stream_u32(slot_out + base + (u64)j * HA_THREADS + tid, (u32)sl);
-                    ok[j] = false;
-                } else {
-                    pending = true;
-                }
-            }
-            if (pending) {
-#pragma unroll
-                for (int j = 0; j < HA_ROWS; ++j)
-                    if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
-            }
-        }
-        if (pending) atomicExch(&ctl->abort, 1u);   // probe chain longer than HA_MAX_PROBE buckets
+        ha_process_rows<OPK, TX, CACHE, HA_ROWS>(t, ctl, k, v, ok, base + tid, slot_out, hc_keys, hc_acc, use_cache, my_inserts, my_hits);
         if ((iter & 15u) == 15u) {   // periodic load-factor check (+ cache verdict); iter is CTA-uniform
             u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
             my_inserts = 0;
@@ -322,6 +332,163 @@ hash_agg_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Tab
     u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
     if ((tid & 31u) == 0 && w) atomicAdd(&s_inserts, w);
     __syncthreads();
+    if (tid == 0 && s_inserts) atomicAdd(&ctl->n_inserted, (unsigned long long)s_inserts);
+}
+
+// ---- bulk-staged variant (TMA engine) ---------------------------------------------------------------
+// Same aggregation, different input path.  ncu on the register-staged kernel above shows the SM's
+// L1TEX→XBAR request port as the busiest unit (l1tex__m_l1tex2xbar_req_cycles_active 81 %; one request
+// per cycle per SM, and a random probe, a RED and every 128 B of the stream each cost one), with the
+// port idle whenever all resident CTAs sit in the DRAM-latency phase of their tile.  Here a producer
+// warp keeps HB_STAGES input tiles in flight per CTA with cp.async.bulk + mbarrier (no registers, no
+// LSU instructions for the stream); the 8 consumer warps only ever wait on L2-latency probes, so the
+// request port stays busy.  Full tiles only (16-byte aligned, 16 KB each); the host sends inputs with
+// unaligned bases to the register-staged kernel, and the sub-tile tail is read with plain loads.
+#ifndef VB_HB_STAGES
+#define VB_HB_STAGES 3
+#endif
+#ifndef VB_HB_ROWS
+#define VB_HB_ROWS 4
+#endif
+#ifndef VB_HB_CTAS
+#define VB_HB_CTAS 3
+#endif
+constexpr int HB_STAGES = VB_HB_STAGES;
+constexpr int HB_ROWS = VB_HB_ROWS;             // rows per consumer thread per tile
+constexpr int HB_TILE = HA_THREADS * HB_ROWS;
+constexpr int HB_THREADS = HA_THREADS + 32;     // 8 consumer warps + 1 producer warp
+constexpr size_t hb_smem_bytes(bool has_vals) { return (size_t)HB_STAGES * HB_TILE * (has_vals ? 16 : 8); }
+
+template <int IN, int OPK, int TX>
+__global__ void __launch_bounds__(HB_THREADS, VB_HB_CTAS)
+hash_agg_bulk_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, Table t, TableCtl *ctl, u64 max_inserts,
+                     u32 *__restrict__ slot_out)
+{
+    static_assert(IN == IN_AOS || IN == IN_SOA, "table merges use hash_agg_kernel");
+    constexpr bool CACHE = VB_HC_ENABLE && (OPK != OPK_DICT);
+    constexpr int OPK_FLUSH = (OPK == OPK_COUNT) ? OPK_ADD_U64 : OPK;
+    constexpr bool HAS_V = (IN == IN_AOS) || (OPK != OPK_COUNT && OPK != OPK_DICT);
+    constexpr u32 STAGE_BYTES = HB_TILE * (HAS_V ? 16 : 8);
+    extern __shared__ __align__(128) unsigned char hb_stage[];      // [HB_STAGES][STAGE_BYTES]
+    __shared__ __align__(8) u64 full_bar[HB_STAGES];
+    __shared__ __align__(8) u64 empty_bar[HB_STAGES];
+    __shared__ u32 s_inserts;
+    __shared__ u32 s_abort;
+    __shared__ u32 s_hits;
+    __shared__ u64 hc_keys[CACHE ? HC_SLOTS : 1];
+    __shared__ u64 hc_acc[CACHE ? HC_SLOTS : 1];
+    const u32 tid = threadIdx.x;
+    if (tid == 0) {
+        s_inserts = 0; s_abort = 0; s_hits = 0;
+#pragma unroll
+        for (int s = 0; s < HB_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], HA_THREADS / 32); }
+        mbar_fence_init();
+    }
+    if (CACHE)
+        for (u32 i = tid; i < HC_SLOTS; i += HB_THREADS) { hc_keys[i] = EMPTY_KEY; hc_acc[i] = op_identity(OPK); }
+    __syncthreads();
+    const u64 n_full = n / HB_TILE;                         // tiles that go through the copy engine
+
+    if (tid >= HA_THREADS) {                                // ===== producer warp =====
+        if (tid == HA_THREADS) {
+            const u64 pol = policy_evict_first();
+            u32 i = 0;
+            for (u64 tile = blockIdx.x; tile < n_full; tile += gridDim.x, ++i) {
+                const u32 s = i % HB_STAGES;
+                if (i >= HB_STAGES) mbar_wait(&empty_bar[s], ((i / HB_STAGES) & 1u) ^ 1u);   // consumers released the slot
+                unsigned char *dst = hb_stage + (size_t)s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                if (IN == IN_AOS) {
+                    bulk_g2s(dst, a + 2 * tile * HB_TILE, STAGE_BYTES, &full_bar[s], pol);
+                } else {
+                    bulk_g2s(dst, a + tile * HB_TILE, HB_TILE * 8, &full_bar[s], pol);
+                    if (HAS_V) bulk_g2s(dst + HB_TILE * 8, b + tile * HB_TILE, HB_TILE * 8, &full_bar[s], pol);
+                }
+            }
+        }
+        return;                                             // every copy it issued is awaited by the consumers below
+    }
+
+    // ===== consumer warps =====
+    u32 my_inserts = 0, my_hits = 0;
+    u32 iter = 0;
+    bool use_cache = CACHE;
+    bool drain = false;        // after an abort: keep the pipeline moving (copies in flight target this CTA's smem), skip the work
+    for (u64 tile = blockIdx.x; tile < n_full; tile += gridDim.x, ++iter) {
+        const u32 s = iter % HB_STAGES;
+        mbar_wait(&full_bar[s], (iter / HB_STAGES) & 1u);
+        const unsigned char *src = hb_stage + (size_t)s * STAGE_BYTES;
+        u64 k[HB_ROWS], v[HB_ROWS];
+        bool ok[HB_ROWS];
+#pragma unroll
+        for (int j = 0; j < HB_ROWS; ++j) {
+            const u32 r = (u32)j * HA_THREADS + tid;
+            ok[j] = !drain;
+            if (IN == IN_AOS) {
+                const ulonglong2 row = reinterpret_cast<const ulonglong2 *>(src)[r];
+                k[j] = row.x; v[j] = row.y;
+            } else {
+                k[j] = reinterpret_cast<const u64 *>(src)[r];
+                v[j] = HAS_V ? reinterpret_cast<const u64 *>(src + HB_TILE * 8)[r] : 0ull;
+            }
+        }
+        __syncwarp();
+        if ((tid & 31u) == 0) mbar_arrive(&empty_bar[s]);   // this warp's rows are in registers: slot may be refilled
+        if (!drain) ha_process_rows<OPK, TX, CACHE, HB_ROWS>(t, ctl, k, v, ok, tile * HB_TILE + tid, slot_out, hc_keys, hc_acc, use_cache, my_inserts, my_hits);
+        if ((iter & 15u) == 15u) {   // periodic load-factor check (+ cache verdict); iter is CTA-uniform
+            u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
+            my_inserts = 0;
+            if ((tid & 31u) == 0 && w) atomicAdd(&s_inserts, w);
+            if (CACHE && iter == 15u) {
+                u32 hw = __reduce_add_sync(0xffffffffu, my_hits);
+                if ((tid & 31u) == 0 && hw) atomicAdd(&s_hits, hw);
+            }
+            named_bar_sync(1, HA_THREADS);
+            if (tid == 0) {
+                u32 c = s_inserts;
+                s_inserts = 0;
+                u64 tot = atomicAdd(&ctl->n_inserted, (unsigned long long)c) + c;
+                u32 ab = ld_volatile_u32(&ctl->abort);
+                if (tot > max_inserts) { ab = 1; atomicExch(&ctl->abort, 1u); }
+                s_abort = ab;
+            }
+            named_bar_sync(1, HA_THREADS);
+            if (s_abort) drain = true;
+            if (CACHE && iter == 15u && s_hits * 16u < 16u * HB_TILE) use_cache = false;
+        }
+    }
+    // tail (< HB_TILE rows): plain loads, by the CTA whose turn it would have been
+    if (!drain && (n % HB_TILE) && blockIdx.x == (u32)(n_full % gridDim.x)) {
+        const u64 pol = policy_evict_first();
+        const u64 base = n_full * HB_TILE;
+        u64 k[HB_ROWS], v[HB_ROWS];
+        bool ok[HB_ROWS];
+#pragma unroll
+        for (int j = 0; j < HB_ROWS; ++j) {
+            const u64 idx = base + (u64)j * HA_THREADS + tid;
+            ok[j] = idx < n;
+            k[j] = 0; v[j] = 0;
+            if (ok[j]) {
+                if (IN == IN_AOS) { ulonglong2 r = ld_stream_u64x2(a + 2 * idx, pol); k[j] = r.x; v[j] = r.y; }
+                else { k[j] = ld_stream_u64(a + idx, pol); if (HAS_V) v[j] = ld_stream_u64(b + idx, pol); }
+            }
+        }
+        ha_process_rows<OPK, TX, CACHE, HB_ROWS>(t, ctl, k, v, ok, base + tid, slot_out, hc_keys, hc_acc, use_cache, my_inserts, my_hits);
+    }
+    if (CACHE) {   // flush the cache into the table (merge op)
+        named_bar_sync(1, HA_THREADS);
+        if (!drain)
+            for (u32 i = tid; i < HC_SLOTS; i += HA_THREADS) {
+                const u64 key = hc_keys[i];
+                if (key == EMPTY_KEY) continue;
+                const u64 hb = home_bucket(key, t.log_cap);
+                u32 slot = 0;
+                if (!table_resolve<OPK_FLUSH>(t, hb, ld_bucket(&t.keys[4 * hb]), key, hc_acc[i], slot, my_inserts)) atomicExch(&ctl->abort, 1u);
+            }
+    }
+    u32 w = __reduce_add_sync(0xffffffffu, my_inserts);
+    if ((tid & 31u) == 0 && w) atomicAdd(&s_inserts, w);
+    named_bar_sync(1, HA_THREADS);
     if (tid == 0 && s_inserts) atomicAdd(&ctl->n_inserted, (unsigned long long)s_inserts);
 }
 

@@ -12,8 +12,11 @@ source-rank-major receive order IS map-id order (group value order, SURVEY.md F5
 reduce ops exchange *combined* rows (≤ distinct keys per rank — map-side combine,
 src/dependency.rs:203-209), group ops exchange raw rows.
 
-The engine is pluggable only so that the exchange logic can be tested on CPU with gloo
-(tests/ plug in an oracle-backed stand-in); the product engine is CudaEngine.
+The exchange itself lives in libvega_b200.so (vb_ctx_comm_init + vb_shuffle_exchange: NCCL grouped
+send/recv, or the fused peer-memory scatter, on the library's stream).  `run_shuffle` calls it whenever the
+context has a communicator; the torch.distributed code paths below remain for the two cases the library's
+NCCL communicator cannot cover: the CPU (gloo) tests of the host logic with an oracle-backed stand-in engine,
+and two ranks sharing ONE GPU on a single-GPU test box (NCCL refuses duplicate devices).
 """
 import ctypes
 
@@ -46,7 +49,7 @@ class CudaEngine:
 
     def map(self, sh, map_id, keys, vals):
         k = keys if isinstance(keys, _Col) else _Col(keys, allow_rows=True)
-        v = None if vals is None else (vals if isinstance(vals, _Col) else _Col(vals))
+        v = None if vals is None else (vals if isinstance(vals, _Col) else _Col(vals, role="value"))
         sh.map(map_id, k, v, 0, k.n)
 
     def export(self, sh, world):
@@ -124,6 +127,7 @@ def p2p_exchange(engine, sh, rank, world, group=None, stats=None):
     tot = (ctypes.c_uint64 * world)(*total_recv)
     L.check(lib.vb_shuffle_export_direct(sh._h, off, tot))        # returns when this rank's stores are done
     dist.barrier(group=group)                                     # everybody's rows have landed
+    L.check(lib.vb_ctx_arena_release_retired(sc._h))              # every peer re-opened: outgrown arenas can go
     rc = (ctypes.c_uint64 * world)(*recv_counts)
     L.check(lib.vb_shuffle_import_arena(sh._h, rc))
     if stats is not None:
@@ -164,7 +168,15 @@ def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, wo
     sh = engine.create(n_map, n_reduce, kcode, vcode, agg, rank, world, key_width=key_width, hint=hint)
     for map_id, keys, vals in local_maps:
         engine.map(sh, map_id, keys, vals)
-    if world > 1 and p2p and agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP) and isinstance(engine, CudaEngine):
+    if world > 1 and isinstance(engine, CudaEngine) and getattr(engine.sc, "comm", None) and exchange_device is None:
+        # the product path: count exchange + ONE grouped NCCL send/recv (or the fused P2P scatter) inside
+        # libvega_b200, on the library's stream; torch.distributed is not involved
+        group_op = agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP)
+        sh.exchange(L.VB_XCHG_P2P if (p2p and group_op) else L.VB_XCHG_NCCL)
+        if stats is not None:
+            for k_, v_ in sh.exchange_stats().items():
+                stats[k_] = (stats.get(k_, 0) + v_) if k_ in ("exchange_ms", "exchanges") else v_
+    elif world > 1 and p2p and agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP) and isinstance(engine, CudaEngine):
         p2p_exchange(engine, sh, rank, world, group, stats)
     elif world > 1:
         counts, sk, sv = engine.export(sh, world)

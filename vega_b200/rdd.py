@@ -42,7 +42,7 @@ def _sync_torch(*tensors):
 class _Col:
     """One 64-bit column (or an (n,2) AoS row block): pointer + location + dtype code."""
 
-    def __init__(self, x, allow_rows=False):
+    def __init__(self, x, allow_rows=False, role="key"):
         self.key_width = 8
         self.rows = False
         if _is_torch(x):
@@ -62,11 +62,15 @@ class _Col:
             shape = tuple(x.shape)
         else:
             x = np.asarray(x)
-            if x.dtype in (np.int32, np.uint32, np.int16, np.uint16, np.int8, np.uint8):
+            if x.dtype in (np.int32, np.uint32):
                 self.key_width = 4          # Rust i32/u32 keys hash as 4 LE bytes
                 x = x.astype(np.int64 if x.dtype.kind == "i" else np.uint64)
-            if x.dtype.kind == "b":
-                x = x.astype(np.uint64)
+            elif x.dtype in (np.int16, np.uint16, np.int8, np.uint8) or x.dtype.kind == "b":
+                # Rust hashes i16 as 2 bytes and i8/u8/bool as 1: the library has 4- and 8-byte key hashes only,
+                # so narrow KEYS would be placed differently from the reference's HashPartitioner — refuse them.
+                if role == "key":
+                    raise TypeError(f"key dtype {x.dtype}: only 32- and 64-bit integer keys hash like the reference's")
+                x = x.astype(np.int64 if x.dtype.kind == "i" else np.uint64)
             code = {"u": L.VB_U64, "i": L.VB_I64, "f": L.VB_F64}.get(x.dtype.kind)
             if code is None or x.dtype.itemsize != 8:
                 raise TypeError(f"unsupported dtype {x.dtype}")
@@ -106,6 +110,7 @@ class Context:
         self._h = h
         self._ids = itertools.count()
         self._shuffles = weakref.WeakSet()      # live shuffles are freed before the context goes away
+        self.comm = None
         if profile:
             self.set_profile(True)
 
@@ -137,9 +142,9 @@ class Context:
         """`sc.parallelize(vec, num_slices)`.  data: 1-D keys (→ Rdd), (n,2) rows or
         (keys, values) (→ PairRdd)."""
         if values is not None:
-            return PairRdd(self, _Col(data), _Col(values), num_slices)
+            return PairRdd(self, _Col(data), _Col(values, role="value"), num_slices)
         if isinstance(data, tuple) and len(data) == 2:
-            return PairRdd(self, _Col(data[0]), _Col(data[1]), num_slices)
+            return PairRdd(self, _Col(data[0]), _Col(data[1], role="value"), num_slices)
         col = _Col(data, allow_rows=True)
         if col.rows:
             return PairRdd(self, col, None, num_slices)
@@ -156,11 +161,39 @@ class Context:
         L.check(self._lib.vb_gen_pairs(self._h, p(out_rows), p(out_keys), p(out_vals), first, n, m, n_distinct,
                                        rank_base, seed_k, seed_v, float(zipf_s)))
 
+    def trim(self, keep_bytes=0):
+        """Return pool memory beyond keep_bytes to the device."""
+        L.check(self._lib.vb_ctx_trim(self._h, keep_bytes))
+
+    # ---- one-process-per-GPU: the NCCL communicator lives inside the library ------------------
+    def comm_init(self, rank, world, unique_id=None, group=None):
+        """Collective.  unique_id: the 128 bytes from `Context.comm_unique_id()` on rank 0, handed to every
+        rank by any host-side bootstrap; if None, torch.distributed (already initialised) broadcasts it —
+        torch is then used for this bootstrap only, the exchange itself runs inside libvega_b200."""
+        if unique_id is None:
+            import torch.distributed as dist
+            box = [self.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            unique_id = box[0]
+        buf = (ctypes.c_ubyte * L.VB_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        L.check(self._lib.vb_ctx_comm_init(self._h, buf, rank, world))
+        self.comm = (rank, world)
+
+    def comm_unique_id(self):
+        buf = (ctypes.c_ubyte * L.VB_UNIQUE_ID_BYTES)()
+        L.check(self._lib.vb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_destroy(self):
+        if getattr(self, "comm", None):
+            L.check(self._lib.vb_ctx_comm_destroy(self._h))
+            self.comm = None
+
     def close(self):
         if self._h:
             for sh in list(self._shuffles):
                 sh.free()
-            self._lib.vb_ctx_destroy(self._h)
+            self._lib.vb_ctx_destroy(self._h)      # collective when a communicator exists
             self._h = None
 
     def __enter__(self):
@@ -201,6 +234,16 @@ class Shuffle:
             if vals is not None and vals.loc != keys.loc:
                 raise ValueError("keys and values must live in the same memory space")
             L.check(self._lib.vb_shuffle_map_soa(self._h, map_id, keys.at(start), vals.at(start) if vals is not None else None, n, keys.loc))
+
+    def exchange(self, mode=L.VB_XCHG_AUTO):
+        """The shuffle's exchange step inside the library (collective; needs Context.comm_init)."""
+        L.check(self._lib.vb_shuffle_exchange(self._h, mode))
+
+    def exchange_stats(self):
+        st = L.vb_xstats()
+        L.check(self._lib.vb_shuffle_exchange_stats(self._h, ctypes.byref(st)))
+        return {"sent_rows": st.sent_rows, "recv_rows": st.recv_rows, "exchanges": st.exchanges,
+                "exchange_ms": st.exchange_ms, "exchange_kind": {0: None, 1: "nccl", 2: "p2p"}[st.kind]}
 
     def seal(self):
         L.check(self._lib.vb_shuffle_seal(self._h))
