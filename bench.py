@@ -89,16 +89,43 @@ class ClockSampler:
         return out
 
 
-def cpu_port_run(n_rows, D, M, R, threads, steps, warmup):
-    """The reference's CPU algorithm (oracle/vega_oracle.c) on `n_rows` rows of the same generator."""
+def cpu_port_run(n_rows, D, M, R, threads, steps, warmup, warm_rows=None):
+    """The reference's CPU algorithm (oracle/vega_oracle.c) on `n_rows` rows of the same generator.
+    warm_rows: warm-up steps run on this many leading rows (the CPU has no caches to warm at these sizes;
+    it keeps a full-size reference run within minutes)."""
     from oracle import oracle as O
     keys, vals = O.gen_uniform(0, n_rows, D, 1, 2)
     times = []
+    w = min(warm_rows or n_rows, n_rows)
     for i in range(warmup + steps):
+        if i < warmup:
+            O.shuffle_timed("sum", keys[:w], vals[:w], M, R, threads=threads)
+            continue
         dt, nk = O.shuffle_timed("sum", keys, vals, M, R, threads=threads)
-        if i >= warmup:
-            times.append(dt)
+        times.append(dt)
     return times
+
+
+def bench_config(workload):
+    """`config` of the JSON line — the same dict for both arms (the reference arm times the same workload)."""
+    return {"workload": workload, "layout": "AoS 16-byte rows resident in HBM", "op": "sum",
+            "l2": "inputs (16 GB/GPU) larger than the 126 MB L2; no flush needed",
+            "timing": "CUDA events on the library's stream, max over ranks"}
+
+
+def traffic_lookup(kernel, rows_per_launch, table_slots):
+    """Measured DRAM bytes per launch of the dominant kernel from the committed ncu table
+    (profiles/traffic_table.json, written from `ncu --set full` captures); None when this exact
+    kernel/config has no capture — never a stale constant."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_table.json")) as f:
+            tab = json.load(f)
+    except Exception:
+        return None, None
+    for e in tab.get("entries", []):
+        if e["kernel"] == kernel and abs(e["rows_per_launch"] - rows_per_launch) < 1 and e["table_slots"] == table_slots:
+            return e["dram_bytes_per_launch"], e["source"]
+    return None, None
 
 
 def main():
@@ -112,7 +139,7 @@ def main():
     ap.add_argument("--maps", type=int, default=8, help="map partitions per GPU")
     ap.add_argument("--reduces", type=int, default=8, help="reduce partitions per GPU")
     ap.add_argument("--e2e-rows", type=float, default=None)
-    ap.add_argument("--cpu-rows", type=float, default=5e7)
+    ap.add_argument("--cpu-rows", type=float, default=None, help="rows per CPU step (default: full size for --impl reference if it fits in minutes, 1e8 for the in-run baseline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -128,25 +155,41 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n_cpu = int(min(args.cpu_rows, N))
         threads = min(M, nproc)
-        times = cpu_port_run(n_cpu, D, M, R, threads, args.steps, args.warmup)
+        # Full-size steps (the configuration the metric is quoted on) when K of them fit in ~4 minutes at the
+        # rate a 1e8-row calibration step shows, else 1e8 rows per step (labelled, not extrapolated).
+        from oracle import oracle as O
+        n_cal = int(min(1e8, N))
+        if args.cpu_rows:
+            n_cpu = int(min(args.cpu_rows, N))
+            n_cal = min(n_cal, n_cpu)
+        else:
+            ck, cv = O.gen_uniform(0, n_cal, D, 1, 2)
+            cal_dt, _ = O.shuffle_timed("sum", ck, cv, M, R, threads=threads)
+            del ck, cv
+            est_full = cal_dt * (N / n_cal) * args.steps
+            try:
+                avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+            except Exception:
+                avail = 0
+            n_cpu = N if (est_full <= 420.0 and avail > 40 * N) else n_cal
+        times = cpu_port_run(n_cpu, D, M, R, threads, args.steps, args.warmup, warm_rows=n_cal)
         tot = sum(times)
         val = n_cpu * len(times) / tot
         line = {
             "impl": "reference", "metric": "reduce_by_key (K,V) pairs/sec", "value": val, "unit": "pairs/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload, "sample": f"each step = the same generator's first {n_cpu:.0e} pairs"},
-            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": f"{n_cpu:.0e} pairs/step, {M}x{R} partitions, C restatement of vega's map-side combine + reduce-side merge (oracle/vega_oracle.c); vega itself is Rust and cannot be built in this image"},
+            "config": bench_config(workload),
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "host_cores": nproc,
+                             "sample": f"{n_cpu:.0e} pairs per timed step ({'the full configuration' if n_cpu == N else 'bounded sample of the same generator'}; warm-up steps on {n_cal:.0e} pairs), {M}x{R} partitions, C restatement of vega's map-side combine + reduce-side merge (oracle/vega_oracle.c); vega itself is Rust and cannot be built in this image"},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
         if nproc > threads:     # informational: the same port with one partition per host core (not this arm's config)
-            t2 = cpu_port_run(n_cpu, D, nproc, nproc, nproc, 2, 1)
-            line["cpu_baseline"]["all_cores"] = {"value": n_cpu * len(t2) / sum(t2), "unit": "pairs/s", "cores": nproc,
-                                                 "partitions": f"{nproc}x{nproc}"}
+            t2 = cpu_port_run(n_cal, D, nproc, nproc, nproc, 2, 1)
+            line["cpu_baseline"]["all_cores"] = {"value": n_cal * len(t2) / sum(t2), "unit": "pairs/s", "cores": nproc,
+                                                 "partitions": f"{nproc}x{nproc}", "sample": f"{n_cal:.0e} pairs"}
         print(json.dumps(line))
         return 0
 
@@ -252,19 +295,22 @@ def main():
         avg_launch_ms = agg["hot_ms"] / max(agg["hot_launches"], 1)
         alg_bytes = rows_per_launch * ALG_BYTES_PER_PAIR + 16.0 * D
         achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+        variant = step_stats[-1].get("hot_kernel_variant", 0)
+        kernel_name = "hash_agg_bulk_kernel<IN_AOS,OPK_ADD_U64>" if variant else "hash_agg_kernel<IN_AOS,OPK_ADD_U64>"
+        traffic, traffic_src = traffic_lookup(kernel_name, rows_per_launch, step_stats[-1].get("table_slots", 0))
         out = {
             "metric": "reduce_by_key (K,V) pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload, "layout": "AoS 16-byte rows resident in HBM", "op": "sum",
-                       "l2": "inputs (16 GB/GPU) larger than the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the library's stream, max over ranks"},
+            "config": bench_config(workload),
             "clocks": clocks,
             "gpu_launches": agg["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (2.4426e9 if abs(rows_per_launch - 1.25e8) < 1 else None),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of 2), ncu --set full, profiles/r1_ncu_hash_agg_final.txt (1.25e8-row launch, 2^22-slot table: the 64 MB table plus the evict-first stream do not fit L2 entirely; lts__throughput 87 % of peak = the L2 is the saturated unit)",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "hash_agg_kernel<IN_AOS,OPK_ADD_U64>",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": kernel_name,
+                         "design_roof": {"what": "an exact streaming aggregation into an L2-resident table needs >= 2 L2 requests per row (probe + RED); measured ceilings with no input stream at all (bench_micro/micro_r2.cu, profiles/r2_micro_request_roof.log): random 32 B loads 2.87e11/s (SM L1TEX->XBAR port, 1 request/clk/SM, l1tex__m_l1tex2xbar_req_cycles_active 97 %), 64-bit REDs 1.97e11/s (lts__t_tag_requests-bound), load+RED pairs 1.255e11 rows/s",
+                                         "rows_per_s": 1.255e11, "GBps": 1.255e11 * 16 / 1e9, "frac_of_hbm_peak": 1.255e11 * 16 / 1e9 / peak,
+                                         "achieved_frac_of_design_roof": achieved / (1.255e11 * 16 / 1e9)},
                          "rows_per_launch": rows_per_launch, "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
                          "step_share": agg["hot_ms"] / max(ms_total, 1e-9),
                          "whole_step_frac": (N * ALG_BYTES_PER_PAIR + 16.0 * D) / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -274,7 +320,7 @@ def main():
         if world > 1:
             sent = xstats.get("sent_rows") or 0
             xms = (xstats.get("exchange_ms") or 0.0) / max(xstats.get("exchanges", 1), 1)
-            out["exchange"] = {"collective": "one all-to-all-v per column (NCCL) of the map-side-combined rows",
+            out["exchange"] = {"collective": "inside libvega_b200 (vb_shuffle_exchange): count all-gather + ONE ncclGroupStart/Send/Recv/GroupEnd carrying both columns of the map-side-combined rows, on the library's stream",
                                "rows_sent_per_rank_per_step": sent, "bytes_sent_per_rank_per_step": 16 * sent,
                                "ms_per_step": xms, "GBps_per_rank": (16 * sent / (xms * 1e-3) / 1e9) if xms > 0 else None,
                                "note": "latency-bound: map-side combine shrinks 16 GB/rank of rows to <= 16 MB"}
@@ -331,7 +377,7 @@ def main():
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = int(min(args.cpu_rows, N))
+        n_cpu = int(min(args.cpu_rows or 1e8, N))
         threads = min(M, nproc)
         times = cpu_port_run(n_cpu, D, M, R, threads, 2, 1)
         out["cpu_baseline"] = {"value": n_cpu * len(times) / sum(times), "unit": "pairs/s", "cores": threads, "kind": "port",

@@ -102,6 +102,7 @@ typedef struct vb_stats {
     uint64_t hot_kernel_rows;  /* rows those launches processed */
     double map_ms;             /* device time inside vb_shuffle_map_* (profiling on) */
     double seal_ms;            /* device time inside vb_shuffle_seal (profiling on) */
+    uint64_t hot_kernel_variant; /* reduce ops: 1 = bulk-staged hash_agg (cp.async.bulk + mbarrier), 0 = register-staged */
 } vb_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

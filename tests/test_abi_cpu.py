@@ -124,6 +124,6 @@ def test_python_constants_match_header_enums():
     for name in ("VB_OK", "VB_ERR_CUDA", "VB_U64", "VB_F64", "VB_AGG_GROUP", "VB_AGG_SORT", "VB_PART_RANGE", "VB_DEVICE_BORROWED", "VB_GEN_UNIQUE"):
         assert name in vals and getattr(L, name) == vals[name]
     # struct layout of vb_stats: 9 u64 + 3 doubles in header order
-    assert ctypes.sizeof(L.vb_stats) == 12 * 8
+    assert ctypes.sizeof(L.vb_stats) == 13 * 8      # 10 u64 + 3 doubles, header order
     fields = re.findall(r"\b(uint64_t|double)\s+(\w+);", src[src.index("typedef struct vb_stats"):src.index("} vb_stats;")])
     assert [f for _, f in fields] == [f for f, _ in L.vb_stats._fields_]

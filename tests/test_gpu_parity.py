@@ -81,6 +81,40 @@ def test_cogroup_and_intersection_golden(sc):
         assert inter == [3, 4, 5, 13]
 
 
+@pytest.mark.parametrize("nparts", [None, 3])
+def test_intersection_api_golden(sc, nparts):
+    # tests/test_rdd.rs:484-521 through the API (Rdd.intersection / intersection_with_num_partitions)
+    first = sc.parallelize(np.array([1, 2, 3, 4, 5, 10, 12, 13, 19, 0], dtype=np.int32), 2)
+    second = sc.parallelize(np.array([3, 4, 5, 6, 7, 8, 11, 13], dtype=np.int32), 4)
+    inter = first.intersection(second, nparts)
+    assert sorted(inter.collect().tolist()) == [3, 4, 5, 13]
+    for r in range(inter.num_slices):         # placement: HashPartitioner over 4-byte keys
+        assert all(O.get_partition(int(x), inter.num_slices, 4) == r for x in inter.compute(r))
+
+
+def test_subtract_api_golden(sc):
+    # tests/test_rdd.rs:675-699
+    first = sc.parallelize(np.array([1, 2, 3, 4, 5, 10, 12, 13, 19, 0], dtype=np.int32), 4)
+    second = sc.parallelize(np.array([3, 4, 5, 6, 7, 8, 11, 13], dtype=np.int32), 4)
+    assert sorted(first.subtract(second).collect().tolist()) == [0, 1, 2, 10, 12, 19]
+
+
+def test_set_ops_match_numpy_on_random_inputs(sc):
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 5000, 40_000).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    b = rng.integers(2500, 9000, 30_000).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    ra, rb = sc.parallelize(a, 5), sc.parallelize(b, 3)
+    assert sorted(ra.intersection(rb, 7).collect().tolist()) == sorted(np.intersect1d(a, b).tolist())
+    assert sorted(ra.subtract(rb).collect().tolist()) == sorted(np.setdiff1d(a, b).tolist())
+
+
+def test_group_by_api_golden(sc):
+    # tests/test_pair_rdd.rs:111-135 through Rdd.group_by(func): neg -> 0, zero -> 1, pos -> 2
+    xs = np.array([-3, -2, -1, 0, 1, 2, 3], dtype=np.int64)
+    g = sc.make_rdd(xs, 2).group_by(lambda x: (np.sign(x) + 1).astype(np.uint64))
+    assert sorted((k, v.tolist()) for k, v in g.collect().to_list()) == [(0, [-3, -2, -1]), (1, [0]), (2, [1, 2, 3])]
+
+
 # ---- randomized differential tests against the oracle -----------------------------------------
 @pytest.mark.parametrize("op,vdtype", [("sum", "u64"), ("sum", "i64"), ("sum", "f64"), ("min", "u64"), ("max", "u64"),
                                        ("min", "i64"), ("max", "i64"), ("min", "f64"), ("max", "f64")])

@@ -91,6 +91,58 @@ def emit(d):
         print(json.dumps(d), flush=True)
 
 
+# ---- oracle-sampled parity at full size -------------------------------------------------------------------
+# A key-closed sample: every row whose key has its low SAMPLE_BITS bits zero (keys are splitmix64 outputs, so this
+# is a uniform ~2^-SAMPLE_BITS sample of the key universe).  Per-key results do not depend on the other keys, so the
+# CPU oracle run on just those rows (all ranks' rows gathered on rank 0, in map-id order) must reproduce the GPU
+# result restricted to those keys — sums, placement (hash(k) % R), ordered value lists, join rows.
+def sample_mask(keys, bits):
+    return (keys & ((1 << bits) - 1)) == 0
+
+
+def gather_sample(rows, bits, cap=4_000_000):
+    """This rank's sampled rows (host numpy, input order); None if the sample is too large to ship."""
+    m = sample_mask(rows[:, 0], bits)
+    n = int(m.sum().item())
+    if n > cap:
+        return None
+    sub = rows[m].cpu().numpy().view(np.uint64)
+    return sub
+
+
+def gather_objs(obj):
+    if world == 1:
+        return [obj]
+    out = [None] * world
+    tdist.all_gather_object(out, obj)
+    return out
+
+
+def oracle_sampled_reduce(rows, bits, R, got_parts):
+    """got_parts: {r: (keys u64, sums u64)} of the partitions this rank owns (already restricted to the sample).
+    Returns (#keys compared, ok) on rank 0, (0, None) elsewhere."""
+    subs = gather_objs(gather_sample(rows, bits))
+    gots = gather_objs(got_parts)
+    if rank != 0:
+        return 0, None
+    if any(x is None for x in subs):
+        return 0, None
+    from oracle import oracle as O
+    allrows = np.concatenate(subs) if len(subs) else np.zeros((0, 2), np.uint64)
+    want = O.shuffle("sum", np.ascontiguousarray(allrows[:, 0]), np.ascontiguousarray(allrows[:, 1]), 8, R, threads=8)
+    got = {}
+    for g in gots:
+        got.update(g)
+    n, ok = 0, True
+    for r in range(R):
+        w = dict(zip(want[r]["keys"].tolist(), want[r]["combined"].tolist()))
+        gk, gc = got.get(r, (np.zeros(0, np.uint64), np.zeros(0, np.uint64)))
+        g = dict(zip(gk.tolist(), gc.tolist()))
+        ok = ok and (g == w)
+        n += len(w)
+    return n, ok
+
+
 ops = args.ops.split(",")
 if "zipf" in ops:
     rows = torch.empty((N, 2), dtype=torch.int64, device=dev)
@@ -102,16 +154,25 @@ if "zipf" in ops:
         st = {}
         sh = shuffle(rows, 8, R, L.VB_AGG_SUM, st)
         nk, sm = 0, 0
+        samp = {}
         for r in vdist.owned_partitions(rank, world, R):
             k, c = sh.reduce(r)
             nk += len(k); sm += int(c.sum(dtype=np.uint64))
+            ku = k.view(np.uint64)
+            msk = (ku & np.uint64((1 << SB) - 1)) == 0
+            samp[r] = (ku[msk].copy(), c.view(np.uint64)[msk].copy())
         sh.free()
-        return nk, sm, st
+        return nk, sm, st, samp
 
-    dt, (nk, sm, st) = timed(run)
+    SB = 10                                     # ~1/1024 of the keys; the Zipf head keys (millions of rows each) are
+    while SB < 20 and int(sample_mask(rows[:, 0], SB).sum().item()) > 4_000_000:   # checked via the total-sum property
+        SB += 1
+    dt, (nk, sm, st, samp) = timed(run)
     keys_total, sum_total = allsum(float(nk)), allsum(float(sm))
+    n_cmp, ok = oracle_sampled_reduce(rows, SB, R, samp)
     emit({"op": "reduce_by_key(sum) Zipf(1.1) [configs[4]]", "n_gpus": world, "rows_total": N * world, "partitions": R, "s": dt,
           "rows_per_s": N * world / dt, "distinct_keys_out": int(keys_total), "sum_matches_input": abs(sum_total - total_vals) < 0.5,
+          "parity": "oracle-sampled", "parity_keys_compared": n_cmp, "parity_ok": ok, "parity_sample": f"keys with low {SB} bits zero: every row of those keys from all ranks -> oracle/vega_oracle.c on rank 0 -> per-partition (key, sum) dicts must be equal",
           "exchange_ms": st.get("exchange_ms"), "bytes_sent_per_rank": 16 * st.get("sent_rows", 0),
           "note": "time includes the D2H read-back of every owned partition"})
     del rows
@@ -157,6 +218,7 @@ if "join" in ops:
         sa = shuffle(a, 1, R, L.VB_AGG_COGROUP, st)
         sb = shuffle(b, 1, R, L.VB_AGG_COGROUP, st)
         tot = 0
+        samp = {}
         for r in vdist.owned_partitions(rank, world, R):
             nn = ctypes.c_uint64()
             L.check(sc._lib.vb_join_size(sa._h, sb._h, r, ctypes.byref(nn)))
@@ -164,14 +226,37 @@ if "join" in ops:
             p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
             L.check(sc._lib.vb_join(sa._h, sb._h, r, p(k), p(v), p(w), L.VB_DEVICE))
             tot += nn.value
+            msk = sample_mask(k, JB)
+            samp[r] = tuple(x[msk].cpu().numpy().view(np.uint64) for x in (k, v, w))
         sa.free(); sb.free()
-        return tot, st
+        return tot, st, samp
 
-    dt, (tot, st) = timed(run)
+    JB = 6                                       # 1/64 of the keys of both sides
+    while JB < 20 and int(sample_mask(a[:, 0], JB).sum().item()) > 2_000_000:
+        JB += 1
+    dt, (tot, st, samp) = timed(run)
     out_rows = int(allsum(float(tot)))
     sent = 16 * st.get("sent_rows", 0)
+    # oracle-sampled parity: the sampled rows of both sides from every rank -> O.join on rank 0 -> every (k, v, w) row
+    sa_, sb_ = gather_objs(gather_sample(a, JB)), gather_objs(gather_sample(b, JB))
+    gots = gather_objs(samp)
+    n_cmp, ok = 0, None
+    if rank == 0 and all(x is not None for x in sa_ + sb_):
+        from oracle import oracle as O
+        fa, fb = np.concatenate(sa_), np.concatenate(sb_)
+        want = O.join(np.ascontiguousarray(fa[:, 0]), np.ascontiguousarray(fa[:, 1]), world, np.ascontiguousarray(fb[:, 0]),
+                      np.ascontiguousarray(fb[:, 1]), world, R, threads=8)
+        got = {}
+        for g in gots:
+            got.update(g)
+        ok = True
+        for r in range(R):
+            g = got.get(r, (np.zeros(0, np.uint64),) * 3)
+            ok = ok and sorted(zip(*[x.tolist() for x in g])) == sorted(zip(*[x.tolist() for x in want[r]]))
+            n_cmp += len(want[r][0])
     emit({"op": "join unique keys [configs[3]]" + (" [p2p]" if args.p2p else " [NCCL]"), "n_gpus": world, "rows_per_side_total": n * world, "partitions": R, "s": dt,
           "input_rows_per_s": 2 * n * world / dt, "join_rows": out_rows, "join_rows_expected": shared_total,
+          "parity": "oracle-sampled", "parity_rows_compared": n_cmp, "parity_ok": ok, "parity_sample": f"keys with low {JB} bits zero on both sides: all their rows -> oracle join on rank 0 -> every (k,v,w) output row per reduce partition must be equal",
           "exchange_ms_both_sides": st.get("exchange_ms"), "bytes_sent_per_rank_last_side": sent})
 sc.close()
 if world > 1:

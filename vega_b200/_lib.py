@@ -34,7 +34,7 @@ class vb_stats(ctypes.Structure):
         ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64), ("table_slots", ctypes.c_uint64),
         ("table_restarts", ctypes.c_uint64), ("hot_kernel_ms", ctypes.c_double),
         ("hot_kernel_launches", ctypes.c_uint64), ("hot_kernel_rows", ctypes.c_uint64),
-        ("map_ms", ctypes.c_double), ("seal_ms", ctypes.c_double),
+        ("map_ms", ctypes.c_double), ("seal_ms", ctypes.c_double), ("hot_kernel_variant", ctypes.c_uint64),
     ]
 
 

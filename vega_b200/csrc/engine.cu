@@ -14,6 +14,7 @@
 
 #include "../../include/vega_b200.h"
 #include "kernels.cuh"
+#include "sweep.cuh"
 
 using namespace vb;
 
@@ -427,6 +428,7 @@ static int launch_hash_agg_t(vb_shuf *s, int klass, const u64 *a, const u64 *b, 
             int occ = occupancy(c, kb, HB_THREADS, smem);
             u64 grid = std::min<u64>(n / HB_TILE, (u64)c->sm_count * occ);
             KLaunch kl(s, klass, n);
+            if (klass == K_HASH_AGG) s->st.hot_kernel_variant = 1;
             kb<<<(unsigned)grid, HB_THREADS, smem, c->stream>>>(a, b, n, table_at(tab, log_cap), ctl, max_inserts, slot_out);
             return kl.done("hash_agg_bulk_kernel");
         }
@@ -788,6 +790,102 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     return VB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sweep pass (sweep.cuh): one kernel per pass, decoupled look-back, copy-engine staged input
+// ---------------------------------------------------------------------------------------------
+#define SW_COMBOS_U64V(X) X(LD_SOA64, DG_BITS) X(LD_AOS64, DG_BITS) X(LD_SOA64, DG_DEST) X(LD_AOS64, DG_DEST) X(LD_SOA64, DG_HASHTOP) X(LD_AOS64, DG_HASHTOP) X(LD_SOA64, DG_BUCKET)
+#define SW_COMBOS_U64K(X) X(LD_SOA64, DG_BITS)
+#define SW_COMBOS_U32V(X) X(LD_KEY32_VAL_SOA, DG_BITS) X(LD_KEY32_VAL_AOS, DG_BITS)
+
+template <typename KeyT, bool HAS_VAL>
+static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist, size_t *smem)
+{
+#define X(L, D)                                                                                   \
+    if (ldm == L && dgm == D) {                                                                   \
+        *kern = (const void *)rp_sweep_kernel<KeyT, HAS_VAL, L, D>;                               \
+        *hist = (const void *)sw_hist_all_kernel<KeyT, L, D>;                                     \
+        *smem = SwSmem<KeyT, HAS_VAL, L>::total;                                                  \
+        return true;                                                                              \
+    }
+    if constexpr (sizeof(KeyT) == 8 && HAS_VAL) { SW_COMBOS_U64V(X) }
+    if constexpr (sizeof(KeyT) == 8 && !HAS_VAL) { SW_COMBOS_U64K(X) }
+    if constexpr (sizeof(KeyT) == 4 && HAS_VAL) { SW_COMBOS_U32V(X) }
+#undef X
+    return false;
+}
+
+static bool sweep_enabled()
+{
+    static const bool off = getenv("VEGA_B200_NO_SWEEP") != nullptr;
+    return !off;
+}
+
+// rows of `ld` must be a plain row stream (every row valid) with 16-byte aligned column bases
+template <typename KeyT, bool HAS_VAL>
+static bool sweep_applicable(const Loader &ld, const Digit &dg, u64 n)
+{
+    const void *k, *h; size_t sm;
+    if (!sweep_enabled() || n == 0 || n >= SW_MAX_ROWS) return false;
+    if (!sweep_lookup<KeyT, HAS_VAL>(ld.mode, dg.mode, &k, &h, &sm)) return false;
+    if (((uintptr_t)ld.keys & 15u) || (ld.vals && ((uintptr_t)ld.vals & 15u))) return false;
+    return true;
+}
+
+// Global histogram of `n_pos` digit positions in one read of the keys, scanned in place: d_bases[p][256].
+template <typename KeyT, bool HAS_VAL>
+static int sweep_hist(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, const HistAllArgs &ha, u32 *d_bases)
+{
+    vb_ctx *c = s->ctx;
+    const void *kern, *hk; size_t smem;
+    if (!sweep_lookup<KeyT, HAS_VAL>(ld.mode, dg.mode, &kern, &hk, &smem)) return set_err(VB_ERR_UNSUPPORTED, "sweep: loader %d / digit %d not instantiated", ld.mode, dg.mode);
+    CU(cudaMemsetAsync(d_bases, 0, (size_t)ha.n_pos * SW_NB * 4, c->stream));
+    Loader ldc = ld; Digit dgc = dg; HistAllArgs hac = ha;
+    {
+        KLaunch kl(s, K_RP_HIST, n);
+        const unsigned grid = (unsigned)std::min<u64>((n + 2047) / 2048, (u64)c->sm_count * 4);
+        void *args[] = {&ldc, &dgc, &n, &hac, &d_bases};
+        CU(cudaLaunchKernel(hk, dim3(grid), dim3(512), args, 0, c->stream));
+        TRY(kl.done("sw_hist_all_kernel"));
+    }
+    {
+        KLaunch kl(s, K_RP_SCAN);
+        sw_scan_bases_kernel<<<ha.n_pos, SW_NB, 0, c->stream>>>(d_bases, ha.n_pos);
+        TRY(kl.done("sw_scan_bases_kernel"));
+    }
+    return VB_OK;
+}
+
+// One stable pass with the digit bases already on the device.  `scratch` (>= sweep_scratch_bytes) is reused across passes.
+template <typename KeyT, bool HAS_VAL>
+static size_t sweep_scratch_bytes(u64 n)
+{
+    const u64 tiles = (n + sw_tile<KeyT, HAS_VAL>() - 1) / sw_tile<KeyT, HAS_VAL>();
+    return (size_t)(tiles * SW_NB + 4) * 4;
+}
+
+template <typename KeyT, bool HAS_VAL>
+static int sweep_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, const u32 *d_base, u32 *scratch)
+{
+    vb_ctx *c = s->ctx;
+    const void *kern, *hk; size_t smem;
+    if (!sweep_lookup<KeyT, HAS_VAL>(ld.mode, dg.mode, &kern, &hk, &smem)) return set_err(VB_ERR_UNSUPPORTED, "sweep: loader %d / digit %d not instantiated", ld.mode, dg.mode);
+    const u32 T = sw_tile<KeyT, HAS_VAL>();
+    const u32 tiles = (u32)((n + T - 1) / T);
+    CU(cudaMemsetAsync(scratch, 0, sweep_scratch_bytes<KeyT, HAS_VAL>(n), c->stream));
+    if (c->occ_cache.find(kern) == c->occ_cache.end()) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int occ = occupancy(c, kern, SW_THREADS, smem);
+    SweepArgs a;
+    a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = tiles;
+    a.tile_counter = scratch; a.state = scratch + 4;
+    a.digit_base = d_base; a.out_keys = out_keys; a.out_vals = out_vals;
+    Digit dgc = dg;
+    KLaunch kl(s, K_RP_SCATTER, n);
+    const unsigned grid = (unsigned)std::min<u64>(tiles, (u64)c->sm_count * occ);
+    void *args[] = {&a, &dgc};
+    CU(cudaLaunchKernel(kern, dim3(grid), dim3(SW_THREADS), args, smem, c->stream));
+    return kl.done("rp_sweep_kernel");
+}
+
 static int launch_hash_agg_partitioned(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
                                        u32 log_cap, TableCtl *ctl, u64 mi)
 {
@@ -803,6 +901,15 @@ static int launch_hash_agg_partitioned(vb_shuf *s, int klass, int in, int opk, i
     dg.mode = DG_HASHTOP;
     dg.shift = 64 - pbits;
     dg.mask = (1u << pbits) - 1;
+    if (sweep_applicable<u64, true>(ld, dg, n)) {
+        DevBuf bases(c), scratch(c);
+        TRY(bases.alloc(SW_NB * 4));
+        TRY(scratch.alloc((sweep_scratch_bytes<u64, true>(n))));
+        HistAllArgs ha{}; ha.n_pos = 1;
+        TRY((sweep_hist<u64, true>(s, ld, dg, n, ha, bases.as<u32>())));
+        TRY((sweep_pass<u64, true>(s, ld, dg, n, tk.as<u64>(), tv.as<u64>(), bases.as<u32>(), scratch.as<u32>())));
+        return launch_hash_agg(s, klass, IN_SOA, opk, tx, tk.as<u64>(), tv.as<u64>(), n, tab, log_cap, ctl, mi, nullptr);
+    }
     TRY((radix_pass<u64, true>(s, ld, dg, n, tk.as<u64>(), tv.as<u64>(), hist.as<u32>(), plan)));
     // stream-ordered frees: the buffers outlive the kernels queued on c->stream
     return launch_hash_agg(s, klass, IN_SOA, opk, tx, tk.as<u64>(), tv.as<u64>(), n, tab, log_cap, ctl, mi, nullptr);
@@ -849,6 +956,23 @@ static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, 
     vb_ctx *c = s->ctx;
     bin_off.assign((size_t)nbins + 1, 0);
     if (n == 0) return VB_OK;
+    if (nbins <= RP_NB) {
+        Digit dg = make_bucket_digit(s, mode, 0, 0xFFFFFFFFu);
+        if (sweep_applicable<u64, true>(ld, dg, n)) {          // row streams: one look-back pass + one histogram read
+            DevBuf bases(c), scratch(c);
+            TRY(bases.alloc(SW_NB * 4));
+            TRY(scratch.alloc((sweep_scratch_bytes<u64, true>(n))));
+            HistAllArgs ha{}; ha.n_pos = 1;
+            TRY((sweep_hist<u64, true>(s, ld, dg, n, ha, bases.as<u32>())));
+            TRY((sweep_pass<u64, true>(s, ld, dg, n, out_keys, out_vals, bases.as<u32>(), scratch.as<u32>())));
+            u32 *h = (u32 *)c->h_scratch;
+            CU(cudaMemcpyAsync(h, bases.p, SW_NB * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (u32 d = 0; d < nbins; ++d) bin_off[d] = h[d];
+            bin_off[nbins] = n;
+            return VB_OK;
+        }
+    }
     PassPlan plan = plan_pass<u64, true>(c, n, 8);
     DevBuf hist(c);
     TRY(hist.alloc(plan.hist_bytes()));
@@ -899,6 +1023,45 @@ static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32
 {
     vb_ctx *c = s->ctx;
     const u32 passes = std::max<u32>(1, (bits + RP_SORT_BITS - 1) / RP_SORT_BITS);
+    {
+        Loader probe = first;
+        probe.keys = ids_a;
+        Digit dgp{};
+        dgp.mode = DG_BITS;
+        if (sweep_applicable<u32, true>(probe, dgp, n) && RP_SORT_BITS == 8) {
+            // sweep path: ONE histogram read for all digit positions, then one look-back kernel per pass
+            DevBuf bases(c), scratch(c), ids_b(c), vals_a(c), vals_b(c);
+            TRY(bases.alloc((size_t)passes * SW_NB * 4));
+            TRY(scratch.alloc((sweep_scratch_bytes<u32, true>(n))));
+            TRY(ids_b.alloc(n * 4));
+            TRY(vals_b.alloc(n * 8));
+            if (passes >= 2) TRY(vals_a.alloc(n * 8));
+            HistAllArgs ha{};
+            ha.n_pos = passes;
+            for (u32 p = 0; p < passes; ++p) ha.shifts[p] = 8 * p;
+            Loader lk{LD_KEY32_VAL_SOA, ids_a, nullptr, 0};
+            TRY((sweep_hist<u32, true>(s, lk, dgp, n, ha, bases.as<u32>())));
+            u32 *src_ids = ids_a, *dst_ids = ids_b.as<u32>();
+            u64 *src_vals = nullptr, *dst_vals = vals_b.as<u64>();
+            for (u32 p = 0; p < passes; ++p) {
+                Loader ld = first;
+                if (p == 0) ld.keys = src_ids;
+                else ld = Loader{LD_KEY32_VAL_SOA, src_ids, src_vals, 0};
+                Digit dg{};
+                dg.mode = DG_BITS; dg.shift = 8 * p; dg.mask = 0xFF; dg.tx = TX_NONE;
+                TRY((sweep_pass<u32, true>(s, ld, dg, n, dst_ids, dst_vals, bases.as<u32>() + (size_t)p * SW_NB, scratch.as<u32>())));
+                std::swap(src_ids, dst_ids);
+                u64 *nv = (src_vals == nullptr) ? vals_a.as<u64>() : src_vals;
+                src_vals = dst_vals;
+                dst_vals = nv;
+            }
+            *out_ids = src_ids;
+            *out_vals = src_vals;
+            if (src_ids == ids_b.as<u32>()) ids_b.release();
+            if (src_vals == vals_b.as<u64>()) vals_b.release(); else vals_a.release();
+            return VB_OK;
+        }
+    }
     PassPlan plan = plan_pass<u32, true>(c, n, RP_SORT_BITS);
     DevBuf hist(c), ids_b(c), vals_a(c), vals_b(c);
     TRY(hist.alloc(plan.hist_bytes()));
@@ -1354,13 +1517,57 @@ static int seal_sort(vb_shuf *s, const Gathered &g)
     TRY(ka.alloc(n * 8));
     TRY(kb.alloc(n * 8));
     if (has_val) { TRY(va.alloc(n * 8)); TRY(vbuf.alloc(n * 8)); }
-    PassPlan plan = has_val ? plan_pass<u64, true>(c, n, RP_SORT_BITS) : plan_pass<u64, false>(c, n, RP_SORT_BITS);
-    TRY(hist.alloc(plan.hist_bytes()));
     u64 *src_k = nullptr, *src_v = nullptr, *dst_k = ka.as<u64>(), *dst_v = va.as<u64>();
     constexpr u32 SORT_PASSES = (64 + RP_SORT_BITS - 1) / RP_SORT_BITS;
+    bool swept = false;
+    {
+        Loader l0 = g.rows ? Loader{LD_AOS64, g.rows, nullptr, 0} : Loader{LD_SOA64, g.keys, g.vals, 0};
+        Digit dgp{};
+        dgp.mode = DG_BITS; dgp.tx = tx;
+        const bool ok = RP_SORT_BITS == 8 && (has_val ? sweep_applicable<u64, true>(l0, dgp, n) : sweep_applicable<u64, false>(l0, dgp, n));
+        if (ok) {
+            // sweep path: all 8 digit histograms from ONE read of the keys; a digit on which every key agrees (one bin
+            // holds all n rows) needs no pass; then one look-back kernel per remaining digit
+            DevBuf bases(c), scratch(c);
+            TRY(bases.alloc((size_t)8 * SW_NB * 4));
+            TRY(scratch.alloc(std::max(sweep_scratch_bytes<u64, true>(n), sweep_scratch_bytes<u64, false>(n))));
+            HistAllArgs ha{};
+            ha.n_pos = 8;
+            for (u32 p = 0; p < 8; ++p) ha.shifts[p] = 8 * p;
+            if (has_val) TRY((sweep_hist<u64, true>(s, l0, dgp, n, ha, bases.as<u32>())));
+            else TRY((sweep_hist<u64, false>(s, l0, dgp, n, ha, bases.as<u32>())));
+            u32 *hb = (u32 *)c->h_scratch;
+            CU(cudaMemcpyAsync(hb, bases.p, 8 * SW_NB * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            bool vary[8];
+            u32 n_vary = 0;
+            for (u32 p = 0; p < 8; ++p) {          // exclusive scan of a one-bin histogram: every base is 0 or n
+                vary[p] = false;
+                for (u32 d = 0; d < SW_NB; ++d) { const u32 b = hb[p * SW_NB + d]; if (b != 0 && b != (u32)n) { vary[p] = true; break; } }
+                n_vary += vary[p];
+            }
+            if (n_vary == 0) vary[0] = true;      // at least one pass: it also copies the rows out
+            bool first = true;
+            for (u32 p = 0; p < 8; ++p) {
+                if (!vary[p]) continue;
+                Loader ld = first ? l0 : Loader{LD_SOA64, src_k, has_val ? src_v : nullptr, 0};
+                first = false;
+                Digit dg{};
+                dg.mode = DG_BITS; dg.shift = 8 * p; dg.mask = 0xFF; dg.tx = tx;
+                if (has_val) TRY((sweep_pass<u64, true>(s, ld, dg, n, dst_k, dst_v, bases.as<u32>() + (size_t)p * SW_NB, scratch.as<u32>())));
+                else TRY((sweep_pass<u64, false>(s, ld, dg, n, dst_k, nullptr, bases.as<u32>() + (size_t)p * SW_NB, scratch.as<u32>())));
+                u64 *nk = (src_k == nullptr) ? kb.as<u64>() : src_k;
+                u64 *nv = (src_v == nullptr) ? vbuf.as<u64>() : src_v;
+                src_k = dst_k; src_v = dst_v; dst_k = nk; dst_v = nv;
+            }
+            swept = true;
+        }
+    }
+    PassPlan plan = has_val ? plan_pass<u64, true>(c, n, RP_SORT_BITS) : plan_pass<u64, false>(c, n, RP_SORT_BITS);
+    if (!swept) TRY(hist.alloc(plan.hist_bytes()));
     // digits on which all keys agree are skipped (e.g. 32-bit-range keys take 4 passes, not 8)
     u64 varying = ~0ull;
-    {
+    if (!swept) {
         DevBuf bits(c);
         TRY(bits.alloc(16));
         const unsigned long long init[2] = {0ull, ~0ull};
@@ -1375,7 +1582,7 @@ static int seal_sort(vb_shuf *s, const Gathered &g)
     }
     bool first = true;
     u32 done = 0;
-    for (u32 p = 0; p < SORT_PASSES; ++p) {
+    for (u32 p = 0; p < SORT_PASSES && !swept; ++p) {
         const u64 dmask = (u64)((1u << RP_SORT_BITS) - 1) << (RP_SORT_BITS * p);
         const bool last_chance = (p + 1 == SORT_PASSES) && done == 0;      // at least one pass: it also copies the rows out
         if (!(varying & dmask) && !last_chance) continue;

@@ -505,6 +505,80 @@ class Rdd(_Base):
     def sort(self, num_splits):
         return ShuffledRdd(PairRdd(self.sc, self.keys, None, self.num_slices), "sort", num_splits)
 
+    def intersection(self, other, num_splits=None):
+        """rdd.rs:852-946 `intersection` / `intersection_with_num_partitions`: the reference cogroups
+        (x, None) of both sides and keeps the keys with `v1.len() >= 1 && v2.len() >= 1` — each key once."""
+        return _SetOp(self, other, num_splits or self.number_of_splits_exact(), "and")
+
+    intersection_with_num_partitions = intersection
+
+    def subtract(self, other, num_splits=None):
+        """rdd.rs:838-901 `subtract`: keys of self whose cogroup with `other` has exactly one non-empty side
+        (`(v1.len() >= 1) ^ (v2.len() >= 1)`), intersected with self — i.e. the distinct keys of self not in other."""
+        return _SetOp(self, other, num_splits or self.number_of_splits_exact(), "a_not_b")
+
+    subtract_with_num_partition = subtract
+
+    def group_by(self, func, num_splits=None):
+        """rdd.rs:957-990 `group_by(func)`: map(x -> (func(x), x)).group_by_key(num_splits).  `func` is a
+        vectorised key function over the item array (numpy / torch), e.g. `lambda x: np.sign(x) + 1`
+        — a scalar closure cannot cross into CUDA, the key column it produces can."""
+        owner = self.keys.owner
+        k = func(owner)
+        if not _is_torch(k):
+            k = np.asarray(k)
+        return PairRdd(self.sc, _Col(k), _Col(owner, role="value"), self.num_slices).group_by_key(num_splits or self.number_of_splits_exact())
+
+    group_by_with_num_partitions = group_by
+
+    def number_of_splits_exact(self):
+        return len(slice_starts(self.n, self.num_slices)) - 1
+
+
+class _SetOp:
+    """intersection / subtract as ONE tagged shuffle: side A rows carry the value 1, side B rows 2^32, the
+    map-side combine + merge (hash_agg) sums them, and a key's sum says which sides it occurred on — the same
+    information the reference reads off the two Vec lengths of its cogroup (rdd.rs:877-884, :925-932)."""
+
+    def __init__(self, a, b, num_splits, mode):
+        if a.keys.key_width != b.keys.key_width or a.keys.code != b.keys.code:
+            raise TypeError("both sides must have the same item type")
+        self.a, self.b, self.num_slices, self.mode, self.sc = a, b, num_splits, mode, a.sc
+        self._sh = None
+
+    @staticmethod
+    def _const_like(col, value):
+        if _is_torch(col.owner):
+            import torch
+            t = torch.full((col.n,), value, dtype=torch.int64, device=col.owner.device)
+            return _Col(t, role="value")
+        return _Col(np.full(col.n, value, dtype=np.uint64), role="value")
+
+    def _run(self):
+        if self._sh is not None:
+            return self._sh
+        sa, sb = slice_starts(self.a.n, self.a.num_slices), slice_starts(self.b.n, self.b.num_slices)
+        na, nb = len(sa) - 1, len(sb) - 1
+        sh = Shuffle(self.sc, na + nb, self.num_slices, self.a.keys.code, L.VB_U64, L.VB_AGG_SUM, key_width=self.a.keys.key_width)
+        ta, tb = self._const_like(self.a.keys, 1), self._const_like(self.b.keys, 1 << 32)
+        for m in range(na):
+            sh.map(m, self.a.keys, ta, int(sa[m]), int(sa[m + 1]))
+        for m in range(nb):
+            sh.map(na + m, self.b.keys, tb, int(sb[m]), int(sb[m + 1]))
+        sh.seal()
+        self._sh = sh
+        return sh
+
+    def compute(self, split):
+        k, c = self._run().reduce(split)
+        c = c.view(np.uint64)
+        in_a, in_b = (c & np.uint64(0xFFFFFFFF)) > 0, (c >> np.uint64(32)) > 0
+        return k[in_a & in_b] if self.mode == "and" else k[in_a & ~in_b]
+
+    def collect(self):
+        parts = [self.compute(r) for r in range(self.num_slices)]
+        return np.concatenate(parts) if parts else np.empty(0)
+
 
 class _Distinct:
     def __init__(self, sh):
