@@ -29,7 +29,9 @@
  * boundary (the reference unwrap()s, dependency.rs:191-214).  Host pointers are caller-owned;
  * device memory is library-owned unless passed in as VB_DEVICE*.  Entry points may be called
  * concurrently from arbitrary OS threads (vega runs map tasks on a tokio blocking pool,
- * src/scheduler/local_scheduler.rs:336-352); device work of one context is serialised.
+ * src/scheduler/local_scheduler.rs:336-352).  A context serialises the ENQUEUEING of its device work; a map
+ * call with host input waits for its own completion with the context unlocked, its H2D copies run on a
+ * separate copy stream through two staging halves, so concurrent map tasks keep PCIe and the SMs busy together.
  * Device work runs on the context's own stream (vb_ctx_stream): device buffers handed in must be complete
  * (producer stream synchronised) before the call; results are complete when a call returns.
  * There is NO CPU fallback: without a CUDA device every compute entry returns VB_ERR_CUDA.
@@ -258,6 +260,11 @@ VB_API uint32_t vb_get_partition(uint64_t key, uint32_t key_width, uint32_t n_re
 /* ParallelCollection::slice: writes slice starts (and n as the last entry) into
  * starts[min(n,num_slices)+2] and returns the number of slices (n+1 when n < num_slices).  */
 VB_API uint64_t vb_slice(uint64_t n, uint64_t num_slices, uint64_t *starts);
+
+/* Context::range (src/context.rs:419-431): the u64 sequence (start..=end).step_by(step) as a device-resident
+ * source — SURVEY §8(f) N3: no host array, no H2D.  vb_range_len = number of elements; out_dev holds that many. */
+VB_API uint64_t vb_range_len(uint64_t start, uint64_t end, uint64_t step);
+VB_API int32_t vb_range(vb_ctx *ctx, void *out_dev, uint64_t start, uint64_t end, uint64_t step);
 
 /* ---- synthetic input, generated on the device (bench / parity tests) -------------------- */
 /* Row i (i = first .. first+n-1):

@@ -74,6 +74,23 @@ impl GpuEngine {
     pub fn seal(&self, shuffle_id: usize) {
         if let Some(h) = self.shuffles.get(&shuffle_id) { let _ = check(unsafe { sys::vb_shuffle_seal(h.0) }); }
     }
+    /// Distributed mode (one executor process per GPU): join the NCCL communicator with the 128-byte id the
+    /// master created (`vb_comm_unique_id`) and shipped over the MapOutputTracker channel (map_output_tracker.rs:68-166).
+    pub fn comm_init(&self, unique_id: &[u8; 128], rank: u32, world: u32) {
+        check(unsafe { sys::vb_ctx_comm_init(self.ctx, unique_id.as_ptr() as *const c_void, rank, world) }).expect("vb_ctx_comm_init");
+    }
+    /// ShuffleFetcher::fetch for the whole shuffle at once (shuffle_fetcher.rs:16-119): after this executor's map tasks
+    /// of `shuffle_id` are registered, swap rows with the other executors inside the library (count all-gather + one
+    /// grouped ncclSend/ncclRecv, or the fused peer-memory scatter), then seal.  Collective over the executors.
+    pub fn exchange_and_seal(&self, shuffle_id: usize, rank: u32, world: u32) {
+        if let Some(h) = self.shuffles.get(&shuffle_id) {
+            if world > 1 {
+                let _ = check(unsafe { sys::vb_shuffle_set_dist(h.0, rank, world) });       // before the first map call in real code
+                let _ = check(unsafe { sys::vb_shuffle_exchange(h.0, 0 /* VB_XCHG_AUTO */) });
+            }
+            let _ = check(unsafe { sys::vb_shuffle_seal(h.0) });
+        }
+    }
     /// Drop for ShuffleDependency (the reference never evicts SHUFFLE_CACHE, env.rs:27)
     pub fn free(&self, shuffle_id: usize) {
         if let Some((_, h)) = self.shuffles.remove(&shuffle_id) { unsafe { sys::vb_shuffle_free(h.0) }; }

@@ -47,6 +47,16 @@ extern "C" {
     pub fn vb_shuffle_export_counts(s: *mut vb_shuf, counts: *mut u64) -> i32;
     pub fn vb_shuffle_export_direct(s: *mut vb_shuf, dst_row_offset: *const u64, dst_total_rows: *const u64) -> i32;
     pub fn vb_shuffle_import_arena(s: *mut vb_shuf, counts: *const u64) -> i32;
+    // the exchange inside the library: NCCL communicator per context (unique id handed out by vega's tracker channel)
+    pub fn vb_comm_unique_id(id_out: *mut c_void /* 128 bytes */) -> i32;
+    pub fn vb_ctx_comm_init(ctx: *mut vb_ctx, unique_id: *const c_void, rank: u32, world: u32) -> i32;
+    pub fn vb_ctx_comm_destroy(ctx: *mut vb_ctx) -> i32;
+    pub fn vb_shuffle_exchange(s: *mut vb_shuf, mode: i32 /* VB_XCHG_AUTO = 0 */) -> i32;
+    pub fn vb_ctx_arena_release_retired(ctx: *mut vb_ctx) -> i32;
+    pub fn vb_ctx_trim(ctx: *mut vb_ctx, keep_bytes: u64) -> i32;
+    // device-resident source (Context::range)
+    pub fn vb_range_len(start: u64, end: u64, step: u64) -> u64;
+    pub fn vb_range(ctx: *mut vb_ctx, out_dev: *mut c_void, start: u64, end: u64, step: u64) -> i32;
     pub fn vb_shuffle_free(s: *mut vb_shuf) -> i32;
     pub fn vb_last_error() -> *const c_char;
     pub fn vb_get_partition(key: u64, key_width: u32, n_reduce: u32) -> u32;

@@ -183,3 +183,67 @@ def test_two_rank_join_and_cogroup_match_oracle(Ma, Mb, R, p2p):
             wd = {int(k): w["vals"][int(w["offsets"][i]):int(w["offsets"][i + 1])].tolist() for i, k in enumerate(w["keys"])}
             assert gd == wd, f"cogroup side {side} partition {r}"
     assert total == sum(len(w[0]) for w in want) > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-rank sort_by_key (absent from the reference, SURVEY.md F2: parity against the oracle's stable sort)
+# ---------------------------------------------------------------------------------------------
+def _sort_dataset(kdtype):
+    rng = np.random.default_rng(5)
+    n = 150_000
+    if kdtype == "u64":
+        keys = rng.integers(0, 3000, n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)     # many duplicates
+    elif kdtype == "i64":
+        keys = rng.integers(-(1 << 40), 1 << 40, n).astype(np.int64)
+    else:
+        keys = rng.standard_normal(n)
+    vals = np.arange(n, dtype=np.uint64)          # payload = input position: checks stability
+    return keys, vals
+
+
+def _sort_worker(rank, world, port, kdtype, M, R, payload, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    import vega_b200 as vb
+    from vega_b200 import _lib as L
+    from vega_b200 import dist as vdist
+    keys, vals = _sort_dataset(kdtype)
+    sc = vb.Context(rank)
+    sc.comm_init(rank, world)
+    eng = vdist.CudaEngine(sc)
+    starts = vb.slice_starts(len(keys), M)
+    lo, hi = vdist.map_block(rank, world, M)
+    maps = [(m, keys[starts[m]:starts[m + 1]], vals[starts[m]:starts[m + 1]] if payload else None) for m in range(lo, hi)]
+    kcode = {"u64": L.VB_U64, "i64": L.VB_I64, "f64": L.VB_F64}[kdtype]
+    sh = vdist.run_shuffle(eng, maps, M, R, kcode, L.VB_U64, L.VB_AGG_SORT, rank, world)
+    sh.has_payload = payload
+    res = {r: [None if x is None else np.asarray(x) for x in sh.reduce(r)] for r in range(R)}
+    with open(os.path.join(outdir, f"s{rank}.pkl"), "wb") as f:
+        pickle.dump(res, f)
+    sh.free()
+    sc.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kdtype,M,R,payload", [("u64", 4, 4, True), ("i64", 5, 6, True), ("f64", 2, 3, False), ("u64", 3, 2, False)])
+def test_two_rank_sort_by_key_matches_oracle(kdtype, M, R, payload):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("multi-rank sort_by_key runs through the library's NCCL communicator: needs >= 2 GPUs")
+    from oracle import oracle as O
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_sort_worker, args=(world, _free_port(), kdtype, M, R, payload, d), nprocs=world, join=True)
+        per_rank = [pickle.load(open(os.path.join(d, f"s{r}.pkl"), "rb")) for r in range(world)]
+    keys, vals = _sort_dataset(kdtype)
+    ok, ov, ps = O.sort_by_key(keys, vals if payload else None, R, kdtype)
+    for r in range(R):
+        gk, gv = per_rank[r % world][r]
+        a, b = int(ps[r]), int(ps[r + 1])
+        assert np.array_equal(gk.view(np.uint64), ok[a:b].view(np.uint64)), f"partition {r} keys"
+        if payload:
+            assert np.array_equal(gv.view(np.uint64), ov[a:b]), f"partition {r} payload (stability)"
+        other = per_rank[(r + 1) % world][r]
+        assert len(other[0]) == 0

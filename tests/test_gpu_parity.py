@@ -675,3 +675,74 @@ def test_partition_first_for_tables_larger_than_l2(sc):
         want.update(d)
     assert got == want
     sh.free()
+
+
+# ---- N3: concurrent map tasks, double-buffered H2D staging, device-resident range source -------------------
+def test_concurrent_map_tasks_from_8_threads_match_oracle(sc):
+    """vega runs its map tasks concurrently on a blocking pool (local_scheduler.rs:336-352): 8 OS threads submit the
+    8 map partitions of ONE shuffle at once (host inputs -> the copy-stream staging path), for a reduce op and a
+    group op; results must equal the oracle's, whatever the interleaving."""
+    import threading
+    from vega_b200 import _lib as L
+    from vega_b200.rdd import Shuffle, _Col
+    rng = np.random.default_rng(11)
+    n, M, R = 400_000, 8, 5
+    keys, vals = rand_pairs(rng, n, 20_000)
+    starts = vb.slice_starts(n, M)
+    for agg, op in ((L.VB_AGG_SUM, "sum"), (L.VB_AGG_GROUP, "group")):
+        sh = Shuffle(sc, M, R, L.VB_U64, L.VB_U64, agg)
+        kc, vc = _Col(keys), _Col(vals, role="value")
+        errs = []
+
+        def task(m):
+            try:
+                sh.map(m, kc, vc, int(starts[m]), int(starts[m + 1]))
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=task, args=(m,)) for m in range(M)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errs, errs
+        sh.seal()
+        if op == "sum":
+            want = oracle_reduce("sum", keys, vals, M, R)
+            for r in range(R):
+                k, c = sh.reduce(r)
+                assert dict(zip(k.tolist(), c.tolist())) == want[r]
+        else:
+            want = oracle_group(keys, vals, M, R)
+            for r in range(R):
+                k, o, v = sh.reduce(r)
+                assert {int(kk): v[int(o[i]):int(o[i + 1])].tolist() for i, kk in enumerate(k)} == want[r]
+        sh.free()
+
+
+def test_host_input_larger_than_both_staging_halves(sc):
+    """A host map partition of 20M rows crosses the two 8M-row staging halves more than once (buffer reuse,
+    copy-stream/kernel-stream events); checked by sums and key count against numpy."""
+    n, D = 20_000_000, 50_000
+    rng = np.random.default_rng(5)
+    keys = (rng.integers(0, D, n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    vals = rng.integers(0, 1 << 20, n).astype(np.uint64)
+    k, c = sc.parallelize((keys, vals), 1).reduce_by_key("sum", 3).collect()
+    assert len(k) == len(np.unique(keys)) and int(c.sum(dtype=np.uint64)) == int(vals.sum(dtype=np.uint64))
+    sample = np.unique(keys)[:: D // 64]
+    got = dict(zip(k.tolist(), c.tolist()))
+    for s_ in sample.tolist():
+        assert got[s_] == int(vals[keys == np.uint64(s_)].sum(dtype=np.uint64))
+    rows = np.stack([keys, vals], axis=1)                   # AoS host rows through the same path
+    k2, c2 = sc.parallelize(rows, 2).reduce_by_key("sum", 3).collect()
+    assert dict(zip(k2.tolist(), c2.tolist())) == got
+
+
+def test_range_source_is_generated_on_device(sc):
+    """Context::range (context.rs:419-431): inclusive end, step; count_by_value / distinct over it."""
+    r = sc.range(10, 50, 5, 3)
+    assert r.n == 9
+    assert sorted(r.distinct().collect().tolist()) == list(range(10, 51, 5))
+    k, c = sc.range(0, 999_999, 1, 4).count_by_value().collect()
+    assert len(k) == 1_000_000 and (c == 1).all() and int(k.astype(np.uint64).sum()) == 999_999 * 1_000_000 // 2
+    assert sc.range(5, 4, 1, 2).n == 0

@@ -92,6 +92,8 @@ SYMBOLS = {
     "vb_hash_key": (_u64, [_u64, _u32]),
     "vb_get_partition": (_u32, [_u64, _u32, _u32]),
     "vb_slice": (_u64, [_u64, _u64, _vp]),
+    "vb_range_len": (_u64, [_u64, _u64, _u64]),
+    "vb_range": (_i32, [_vp, _vp, _u64, _u64, _u64]),
     "vb_gen_pairs": (_i32, [_vp, _vp, _vp, _vp, _u64, _u64, _i32, _u64, _u64, _u64, _u64, _dbl]),
     "vb_version": (ctypes.c_char_p, []),
 }

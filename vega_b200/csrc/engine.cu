@@ -2,6 +2,7 @@
 // the shuffle + aggregation kernels in kernels.cuh.  sm_100a only; no CPU fallback: every
 // compute entry needs a CUDA device and fails with VB_ERR_CUDA otherwise.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -62,6 +63,9 @@ struct vb_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // H2D staging copies (overlap the kernels on `stream`)
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_kernel[2] = {nullptr, nullptr}, ev_ready = nullptr;
+    std::vector<void *> pinned_slots;            // 64-byte pinned cells for per-call D2H status words (free list)
     cudaMemPool_t pool = nullptr;
     std::mutex mu;                 // serialises device work of this context
     bool profile = false;
@@ -162,6 +166,16 @@ extern "C" int32_t vb_ctx_create(int32_t device_id, vb_ctx **out)
     uint64_t thr = ~0ull;
     CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     CU(cudaMallocHost(&c->h_scratch, c->h_scratch_bytes));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_kernel[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    {   // the last 4 KiB of the pinned scratch page hold 64 status cells
+        char *base = (char *)c->h_scratch + c->h_scratch_bytes - 4096;
+        for (int i = 0; i < 64; ++i) c->pinned_slots.push_back(base + 64 * i);
+    }
     *out = c;
     return VB_OK;
 }
@@ -180,6 +194,10 @@ extern "C" int32_t vb_ctx_destroy(vb_ctx *c)
     for (void *p : c->retired_arenas) cudaFree(p);
     if (c->arena) cudaFree(c->arena);
     cudaFreeHost(c->h_scratch);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_kernel[i]); }
+    cudaEventDestroy(c->ev_ready);
     cudaStreamDestroy(c->stream);
     if (c->pool) cudaMemPoolDestroy(c->pool);
     delete c;
@@ -293,6 +311,7 @@ struct vb_shuf {
     const u64 *imp_keys = nullptr, *imp_vals = nullptr;
     u64 imp_n = 0;
     u64 *imp_own_k = nullptr, *imp_own_v = nullptr;   // receive buffers of vb_shuffle_exchange (freed with the inputs)
+    std::vector<u64> sort_part_rows;                  // multi-rank sort: exact rows of every output partition this rank owns (0 elsewhere)
     vb_xstats xst{};
     // gathered input kept alive for the reduce side of group ops
     u64 *gath_keys = nullptr, *gath_vals = nullptr;
@@ -305,6 +324,14 @@ struct vb_shuf {
     u32 dict_log_cap = 0;
     u32 *dense_of_slot = nullptr;
     std::map<std::pair<const vb_shuf *, u32>, JoinPlan> join_plans;
+    // COGROUP shuffles are grouped lazily: seal keeps the (owned) rows; the CSR is built by the first reduce call
+    // (cogroup materialisation), or — if a join comes first — only for the keys that occur on BOTH sides.
+    u64 uid = 0;                                   // process-unique id (cache key that survives pointer reuse)
+    bool lazy = false;                             // sealed, rows in lz_*, not grouped yet
+    u64 *lz_keys = nullptr, *lz_vals = nullptr;
+    u64 lz_n = 0;
+    std::vector<vb_shuf *> trash;                  // internal shuffles of a failed filtered join
+    std::map<u64, std::pair<vb_shuf *, vb_shuf *>> filtered;   // by the right side's uid: internal (left, right) shuffles over the matching rows
     // stats
     vb_stats st{};
     std::vector<Timer> timers;
@@ -477,7 +504,38 @@ static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const
     return set_err(VB_ERR_INVALID, "hash_agg: bad input mode %d", in);
 }
 
-constexpr u64 HOST_CHUNK_ROWS = 32ull << 20;   // host inputs are streamed through a 512 MiB stage
+constexpr u64 HOST_CHUNK_ROWS = 8ull << 20;    // host inputs stream through two 128 MiB staging halves (double-buffered)
+
+// vega issues its map tasks concurrently from a tokio blocking pool (local_scheduler.rs:336-352).  A map call holds
+// the context lock while it ENQUEUES copies and kernels, but waits for its own completion (table overflow flag,
+// insert count) with the lock released, so the next task's H2D copies queue up behind this one's without a gap.
+static thread_local std::unique_lock<std::mutex> *tl_ctx_lock = nullptr;
+
+// D2H of `bytes` (<= 64) from `dev` at the current end of c->stream, waited for with the context unlocked.
+static int fetch_status_unlocked(vb_ctx *c, const void *dev, void *out, size_t bytes)
+{
+    if (!tl_ctx_lock || c->pinned_slots.empty()) {          // not inside a map call: plain synchronous fetch
+        CU(cudaMemcpyAsync(c->h_scratch, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        memcpy(out, c->h_scratch, bytes);
+        return VB_OK;
+    }
+    void *slot = c->pinned_slots.back();
+    c->pinned_slots.pop_back();
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaMemcpyAsync(slot, dev, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, c->stream);
+    tl_ctx_lock->unlock();
+    if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+    tl_ctx_lock->lock();
+    cudaSetDevice(c->device);
+    memcpy(out, slot, bytes);
+    c->pinned_slots.push_back(slot);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(VB_ERR_CUDA, "status fetch: %s", cudaGetErrorString(e)); }
+    return VB_OK;
+}
 constexpr u32 MAX_LOG_CAP = 31;
 
 static int launch_hash_agg(vb_shuf *s, int klass, int in, int opk, int tx, const u64 *a, const u64 *b, u64 n, void *tab,
@@ -594,11 +652,16 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
 
     DevBuf ctl(c), stage_a(c), stage_b(c);
     TRY(ctl.alloc(sizeof(TableCtl)));
+    const u64 stage_rows = std::min(max_host, HOST_CHUNK_ROWS);
+    bool half_used[2] = {false, false};
     if (any_host) {
-        u64 rows = std::min(max_host, HOST_CHUNK_ROWS);
-        TRY(stage_a.alloc(rows * 16));   // AoS rows, or SoA keys in the first half / vals in the second
+        TRY(stage_a.alloc(stage_rows * 16));   // per half: AoS rows, or SoA keys in the first 8 B/row / vals in the second
+        TRY(stage_b.alloc(stage_rows * 16));
+        CU(cudaEventRecord(c->ev_ready, c->stream));               // the pool hands the halves out in stream order
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
     }
-    TableCtl *h_ctl = (TableCtl *)c->h_scratch;
+    TableCtl h_ctl_v;
+    TableCtl *h_ctl = &h_ctl_v;
     for (;;) {
         const u64 cap = 1ull << log_cap;
         DevBuf tab(c);
@@ -620,30 +683,38 @@ static int build_table(vb_shuf *s, int klass, const std::vector<AggInput> &input
                 TRY(launch_hash_agg(s, klass, in.in, opk, tx, in.a, in.b, in.n, tab.p, log_cap, ctl.as<TableCtl>(),
                                     max_inserts, slot_out ? slot_out + row_base : nullptr));
             } else {
-                const u64 chunk = std::min(in.n, HOST_CHUNK_ROWS);
-                for (u64 off = 0; off < in.n; off += chunk) {
+                // double-buffered: the copy engine fills one half on the copy stream while hash_agg consumes the other
+                const u64 chunk = std::min(in.n, stage_rows);
+                u32 it = 0;
+                for (u64 off = 0; off < in.n; off += chunk, ++it) {
                     const u64 m = std::min(chunk, in.n - off);
-                    const u64 *da = stage_a.as<u64>(), *db = nullptr;
+                    const u32 hb = it & 1u;
+                    u64 *half = hb ? stage_b.as<u64>() : stage_a.as<u64>();
+                    const u64 *da = half, *db = nullptr;
+                    if (half_used[hb]) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel[hb], 0));   // its last reader is done
                     if (in.in == IN_AOS) {
-                        CU(cudaMemcpyAsync(stage_a.p, in.a + 2 * off, m * 16, cudaMemcpyHostToDevice, c->stream));
+                        CU(cudaMemcpyAsync(half, in.a + 2 * off, m * 16, cudaMemcpyHostToDevice, c->copy_stream));
                         s->st.h2d_bytes += m * 16;
                     } else {
-                        CU(cudaMemcpyAsync(stage_a.p, in.a + off, m * 8, cudaMemcpyHostToDevice, c->stream));
+                        CU(cudaMemcpyAsync(half, in.a + off, m * 8, cudaMemcpyHostToDevice, c->copy_stream));
                         s->st.h2d_bytes += m * 8;
                         if (in.b) {
-                            db = stage_a.as<u64>() + chunk;
-                            CU(cudaMemcpyAsync((void *)db, in.b + off, m * 8, cudaMemcpyHostToDevice, c->stream));
+                            db = half + chunk;
+                            CU(cudaMemcpyAsync((void *)db, in.b + off, m * 8, cudaMemcpyHostToDevice, c->copy_stream));
                             s->st.h2d_bytes += m * 8;
                         }
                     }
+                    CU(cudaEventRecord(c->ev_copied[hb], c->copy_stream));
+                    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[hb], 0));
                     TRY(launch_hash_agg(s, klass, in.in, opk, tx, da, db, m, tab.p, log_cap, ctl.as<TableCtl>(),
                                         max_inserts, nullptr));
+                    CU(cudaEventRecord(c->ev_kernel[hb], c->stream));
+                    half_used[hb] = true;
                 }
             }
             row_base += in.n;
         }
-        CU(cudaMemcpyAsync(h_ctl, ctl.p, sizeof(TableCtl), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        TRY(fetch_status_unlocked(c, ctl.p, h_ctl, sizeof(TableCtl)));     // waits with the context unlocked inside a map call
         if (!h_ctl->abort) {
             *out_tab = tab.release();
             *out_log_cap = log_cap;
@@ -828,6 +899,7 @@ static bool sweep_applicable(const Loader &ld, const Digit &dg, u64 n)
     if (!sweep_enabled() || n == 0 || n >= SW_MAX_ROWS) return false;
     if (!sweep_lookup<KeyT, HAS_VAL>(ld.mode, dg.mode, &k, &h, &sm)) return false;
     if (((uintptr_t)ld.keys & 15u) || (ld.vals && ((uintptr_t)ld.vals & 15u))) return false;
+    if (HAS_VAL && ld.mode != LD_AOS64 && !ld.vals) return false;       // key-only rows in a (key, value) pass: the rp_* kernels fill zeros
     return true;
 }
 
@@ -1108,6 +1180,8 @@ extern "C" int32_t vb_shuffle_create(vb_ctx *c, uint64_t shuffle_id, uint32_t n_
     if ((agg == VB_AGG_SORT) != (part == VB_PART_RANGE)) return set_err(VB_ERR_INVALID, "VB_PART_RANGE goes with VB_AGG_SORT only");
     if (n_reduce > 65536) return set_err(VB_ERR_UNSUPPORTED, "more than 65536 reduce partitions");
     vb_shuf *s = new vb_shuf();
+    static std::atomic<u64> next_uid{1};
+    s->uid = next_uid.fetch_add(1);
     s->ctx = c;
     s->id = shuffle_id;
     s->n_map = n_map;
@@ -1138,7 +1212,6 @@ extern "C" int32_t vb_shuffle_set_hint(vb_shuf *s, uint64_t d)
 extern "C" int32_t vb_shuffle_set_dist(vb_shuf *s, uint32_t rank, uint32_t world)
 {
     if (!s || world < 1 || rank >= world || world > 256) return set_err(VB_ERR_INVALID, "bad rank/world");
-    if (s->agg == VB_AGG_SORT && world > 1) return set_err(VB_ERR_UNSUPPORTED, "multi-rank sort_by_key is not implemented");
     s->rank = rank;
     s->world = world;
     return VB_OK;
@@ -1164,7 +1237,8 @@ static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys,
         std::lock_guard<std::mutex> g(s->mu);
         if (s->sealed || s->exported || s->freed) return set_err(VB_ERR_STATE, "shuffle %llu: map after seal/export", (unsigned long long)s->id);
     }
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::unique_lock<std::mutex> lk(c->mu);
+    struct TlGuard { TlGuard(std::unique_lock<std::mutex> *l) { tl_ctx_lock = l; } ~TlGuard() { tl_ctx_lock = nullptr; } } tlg(&lk);
     CU(cudaSetDevice(c->device));
     KLaunch call(s, -1);
     MapOut &m = s->maps[map_id];
@@ -1224,21 +1298,34 @@ static int shuffle_map(vb_shuf *s, u32 map_id, const u64 *rows, const u64 *keys,
         } else {
             const cudaMemcpyKind kind = loc == VB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
             DevBuf a(c), b(c);
+            // the copies run on the copy stream (ordered after the pool's hand-out), so a concurrent map task's kernels
+            // on c->stream are not held up by this task's PCIe transfer
+            if (rows) TRY(a.alloc(n * 16));
+            else { TRY(a.alloc(n * 8)); if (vals) TRY(b.alloc(n * 8)); }
+            cudaEvent_t ev_in, ev_done;
+            CU(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+            CU(cudaEventRecord(ev_in, c->stream));
+            CU(cudaStreamWaitEvent(c->copy_stream, ev_in, 0));
             if (rows) {
-                TRY(a.alloc(n * 16));
-                CU(cudaMemcpyAsync(a.p, rows, n * 16, kind, c->stream));
+                CU(cudaMemcpyAsync(a.p, rows, n * 16, kind, c->copy_stream));
                 if (loc == VB_HOST) s->st.h2d_bytes += n * 16;
             } else {
-                TRY(a.alloc(n * 8));
-                CU(cudaMemcpyAsync(a.p, keys, n * 8, kind, c->stream));
+                CU(cudaMemcpyAsync(a.p, keys, n * 8, kind, c->copy_stream));
                 if (loc == VB_HOST) s->st.h2d_bytes += n * 8;
                 if (vals) {
-                    TRY(b.alloc(n * 8));
-                    CU(cudaMemcpyAsync(b.p, vals, n * 8, kind, c->stream));
+                    CU(cudaMemcpyAsync(b.p, vals, n * 8, kind, c->copy_stream));
                     if (loc == VB_HOST) s->st.h2d_bytes += n * 8;
                 }
             }
-            CU(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer on return
+            CU(cudaEventRecord(ev_done, c->copy_stream));
+            CU(cudaStreamWaitEvent(c->stream, ev_done, 0));      // later work on c->stream sees the rows
+            lk.unlock();                                         // the caller may reuse its buffer on return: wait, unlocked
+            cudaError_t ce = cudaEventSynchronize(ev_done);
+            lk.lock();
+            cudaSetDevice(c->device);
+            cudaEventDestroy(ev_in); cudaEventDestroy(ev_done);
+            if (ce != cudaSuccess) { cudaGetLastError(); return set_err(VB_ERR_CUDA, "input copy: %s", cudaGetErrorString(ce)); }
             if (rows) m.rows = (const u64 *)a.release();
             else { m.keys = (const u64 *)a.release(); m.vals = vals ? (const u64 *)b.release() : nullptr; }
             m.owned = true;
@@ -2200,6 +2287,159 @@ static int exchange_p2p_locked(vb_shuf *s)
     return VB_OK;
 }
 
+
+// ---- multi-rank sort_by_key -----------------------------------------------------------------------------------
+// (no reference code: sort_by_key is absent from vega, SURVEY.md F2 — semantics = the single-GPU ones: output
+// partition p is the p-th contiguous key range, cut at floor(p*N/R) moved past equal keys, stable.)
+// Every rank sorts its rows locally, the ranks find the EXACT global cut keys by bisection over the key space
+// (64 rounds, each one tiny all-gather of R-1 counts obtained by binary search in the sorted local run), each
+// rank's sorted run is then cut into contiguous segments that travel in ONE grouped send/recv to the owners
+// (partition p lives on rank p % world), and the owner's seal re-sorts what it received (stable: source-rank-major
+// arrival order = map-id order).
+__global__ void count_le_kernel(const u64 *__restrict__ sorted, u64 n, int tx, const u64 *__restrict__ cand, u32 m, u64 *__restrict__ out)
+{
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const u64 v = cand[p];
+    u64 lo = 0, hi = n;                       // first index whose transformed key is > v
+    while (lo < hi) {
+        const u64 mid = lo + ((hi - lo) >> 1);
+        if (tx_fwd(sorted[mid], tx) <= v) lo = mid + 1; else hi = mid;
+    }
+    out[p] = lo;
+}
+
+static int exchange_sort_locked(vb_shuf *s)
+{
+    vb_ctx *c = s->ctx;
+    Comm *m = c->comm;
+    const u32 W = m->world, me = m->rank, R = s->n_reduce;
+    if (R > 4096) return set_err(VB_ERR_UNSUPPORTED, "multi-rank sort_by_key supports up to 4096 output partitions");
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->sealed || s->exported || s->freed) return set_err(VB_ERR_STATE, "export after seal/export");
+    }
+    const int tx = s->kdt == VB_I64 ? TX_I64 : s->kdt == VB_F64 ? TX_F64 : TX_NONE;
+    // 1. local sort
+    Gathered g;
+    TRY(gather_maps(s, &g));
+    const bool has_val = g.rows != nullptr || g.vals != nullptr;
+    TRY(seal_sort(s, g));
+    const u64 n_local = g.n;
+    u64 *lk = s->res_keys, *lv = s->res_comb;
+    s->res_keys = s->res_comb = nullptr; s->n_keys = 0;
+    DevBuf lk_guard(c), lv_guard(c);
+    lk_guard.p = lk; lv_guard.p = lv;
+    // every rank must agree on whether a payload travels (a rank with zero rows has no way to know locally)
+    std::vector<u64> c0(W, 0);
+    c0[0] = n_local; if (W > 1) c0[1] = has_val ? 1 : 0;
+    const u64 *mat = nullptr;
+    TRY(comm_gather_counts(c, c0.data(), &mat));
+    u64 N = 0; bool any_val = false;
+    for (u32 r = 0; r < W; ++r) { N += mat[(size_t)r * (W + 2)]; if (W > 1 && mat[(size_t)r * (W + 2)] && mat[(size_t)r * (W + 2) + 1]) any_val = true; }
+    // 2. exact cut keys: s_p = the key of global rank c_p - 1, c_p = floor(p N / R); rows with key <= s_p go to partitions < p
+    const u32 P = R - 1;
+    std::vector<u64> need(P), lo(P, 0), hi(P, ~0ull), cut(R + 1, 0);
+    std::vector<char> none(P, 0);
+    for (u32 p = 1; p < R; ++p) {
+        const u64 cp = (u64)(((unsigned __int128)p * N) / R);
+        need[p - 1] = cp;                     // need count_le(v) >= c_p  (i.e. >= (c_p - 1) + 1)
+        none[p - 1] = (cp == 0);
+    }
+    DevBuf d_cand(c), d_cnt(c), d_all(c);
+    std::vector<u64> h_all((size_t)W * std::max<u32>(P, 1));
+    if (P) {
+        TRY(d_cand.alloc((size_t)P * 8)); TRY(d_cnt.alloc((size_t)P * 8)); TRY(d_all.alloc((size_t)W * P * 8));
+        std::vector<u64> mid(P);
+        for (int round = 0; round <= 64; ++round) {
+            const bool final_round = (round == 64);
+            for (u32 i = 0; i < P; ++i) mid[i] = final_round ? lo[i] : lo[i] + ((hi[i] - lo[i]) >> 1);
+            CU(cudaMemcpyAsync(d_cand.p, mid.data(), (size_t)P * 8, cudaMemcpyHostToDevice, c->stream));
+            {
+                KLaunch kl(s, K_MISC);
+                count_le_kernel<<<(P + 127) / 128, 128, 0, c->stream>>>(lk, n_local, tx, d_cand.as<u64>(), P, d_cnt.as<u64>());
+                TRY(kl.done("count_le_kernel"));
+            }
+            if (final_round) {                 // local cut positions for the agreed cut keys
+                CU(cudaMemcpyAsync(h_all.data(), d_cnt.p, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                for (u32 i = 0; i < P; ++i) cut[i + 1] = none[i] ? 0 : h_all[i];
+                break;
+            }
+            NC(g_nccl.AllGather(d_cnt.p, d_all.p, P, ncclUint64, m->comm, c->stream));
+            CU(cudaMemcpyAsync(h_all.data(), d_all.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            bool open = false;
+            for (u32 i = 0; i < P; ++i) {
+                u64 tot = 0;
+                for (u32 r = 0; r < W; ++r) tot += h_all[(size_t)r * P + i];
+                if (tot >= need[i]) hi[i] = mid[i]; else lo[i] = mid[i] + 1;
+                open |= lo[i] < hi[i];
+            }
+            if (!open) round = 63;             // converged everywhere: go to the final round
+        }
+    }
+    cut[0] = 0; cut[R] = n_local;
+    for (u32 p = 1; p <= R; ++p) cut[p] = std::max(cut[p], cut[p - 1]);
+    // 3. segment sizes of every rank for every partition
+    std::vector<u64> seg(R);
+    for (u32 p = 0; p < R; ++p) seg[p] = cut[p + 1] - cut[p];
+    DevBuf d_seg(c), d_segall(c);
+    TRY(d_seg.alloc((size_t)R * 8)); TRY(d_segall.alloc((size_t)W * R * 8));
+    std::vector<u64> segall((size_t)W * R);
+    CU(cudaMemcpyAsync(d_seg.p, seg.data(), (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(d_seg.p, d_segall.p, R, ncclUint64, m->comm, c->stream));
+    CU(cudaMemcpyAsync(segall.data(), d_segall.p, (size_t)W * R * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    s->sort_part_rows.assign(R, 0);
+    u64 n_recv = 0;
+    for (u32 p = me; p < R; p += W)
+        for (u32 r = 0; r < W; ++r) { s->sort_part_rows[p] += segall[(size_t)r * R + p]; n_recv += segall[(size_t)r * R + p]; }
+    if (n_recv >= 0xFFFFFFFEull) return set_err(VB_ERR_TOO_LARGE, "rank %u would receive %llu rows", me, (unsigned long long)n_recv);
+    // 4. one grouped send/recv: partition-major, source-rank-major at the receiver
+    DevBuf rk(c), rv(c);
+    TRY(rk.alloc(std::max<u64>(n_recv, 1) * 8));
+    if (any_val) TRY(rv.alloc(std::max<u64>(n_recv, 1) * 8));
+    DevBuf zero_v(c);
+    if (any_val && !lv && n_local) { TRY(zero_v.alloc(n_local * 8)); CU(cudaMemsetAsync(zero_v.p, 0, n_local * 8, c->stream)); lv = zero_v.as<u64>(); }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    NC(g_nccl.GroupStart());
+    for (u32 p = 0; p < R; ++p) {
+        if (!seg[p]) continue;
+        NC(g_nccl.Send(lk + cut[p], seg[p], ncclUint64, (int)(p % W), m->comm, c->stream));
+        if (any_val) NC(g_nccl.Send(lv + cut[p], seg[p], ncclUint64, (int)(p % W), m->comm, c->stream));
+    }
+    u64 off = 0, sent = 0;
+    for (u32 p = me; p < R; p += W)
+        for (u32 r = 0; r < W; ++r) {
+            const u64 cnt = segall[(size_t)r * R + p];
+            if (!cnt) continue;
+            NC(g_nccl.Recv(rk.as<u64>() + off, cnt, ncclUint64, (int)r, m->comm, c->stream));
+            if (any_val) NC(g_nccl.Recv(rv.as<u64>() + off, cnt, ncclUint64, (int)r, m->comm, c->stream));
+            off += cnt;
+        }
+    NC(g_nccl.GroupEnd());
+    if (e0) {
+        cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        s->xst.exchange_ms += ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    for (u32 p = 0; p < R; ++p) if (p % W != me) sent += seg[p];
+    s->xst.sent_rows += sent;
+    s->xst.recv_rows += n_recv - [&] { u64 own = 0; for (u32 p = me; p < R; p += W) own += seg[p]; return own; }();
+    s->xst.exchanges += 1;
+    s->xst.kind = VB_XCHG_NCCL;
+    s->imp_own_k = (u64 *)rk.release();
+    s->imp_own_v = any_val ? (u64 *)rv.release() : nullptr;
+    s->imp_keys = s->imp_own_k; s->imp_vals = s->imp_own_v; s->imp_n = n_recv;
+    s->imported = true;
+    std::lock_guard<std::mutex> gg(s->mu);
+    s->exported = true;
+    return VB_OK;
+}
+
 extern "C" int32_t vb_shuffle_exchange(vb_shuf *s, int32_t mode)
 {
     if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
@@ -2212,6 +2452,7 @@ extern "C" int32_t vb_shuffle_exchange(vb_shuf *s, int32_t mode)
     if (mode == VB_XCHG_P2P && !is_group_op(s->agg)) return set_err(VB_ERR_UNSUPPORTED, "the fused P2P exchange is for GROUP/COGROUP shuffles");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    if (s->agg == VB_AGG_SORT) return exchange_sort_locked(s);
     return mode == VB_XCHG_P2P ? exchange_p2p_locked(s) : exchange_nccl_locked(s);
 }
 
@@ -2219,6 +2460,239 @@ extern "C" int32_t vb_shuffle_exchange_stats(vb_shuf *s, vb_xstats *out)
 {
     if (!s || !out) return set_err(VB_ERR_INVALID, "NULL argument");
     *out = s->xst;
+    return VB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// lazy COGROUP + semi-join filter (CoGroupedRdd::compute + join, co_grouped_rdd.rs:206-249 / pair_rdd.rs:104-121)
+// The reference cogroups both parents completely and then keeps the keys with values on both sides.  Grouping is the
+// expensive part (dictionary + stable sort of every row), and an inner join only needs it for the keys that match:
+// for BASELINE configs[3] that is 2 % of the rows.  So seal of a COGROUP shuffle only takes ownership of the rows;
+// vb_join* first finds the matching keys (dictionary of the right keys, one probe per left row), compacts both sides
+// to the matching rows (stable) and groups just those.  vb_shuffle_reduce* (the cogroup itself) groups everything.
+// ---------------------------------------------------------------------------------------------
+static bool lazy_cogroup_enabled()
+{
+    static const bool off = getenv("VEGA_B200_EAGER_COGROUP") != nullptr;
+    return !off;
+}
+
+// take ownership of the gathered rows as SoA (copy when they are borrowed, in the shared arena, or AoS)
+static int seal_lazy(vb_shuf *s, const Gathered &g, bool rows_are_owned_imports)
+{
+    vb_ctx *c = s->ctx;
+    const u32 R = s->n_reduce;
+    s->bucket_off.assign((size_t)R + 1, 0);
+    s->val_off.assign((size_t)R + 1, 0);
+    s->lz_n = g.n;
+    s->lazy = true;
+    if (g.n == 0) return VB_OK;
+    if (rows_are_owned_imports) {                      // NCCL receive buffers: just keep them
+        s->lz_keys = s->imp_own_k; s->lz_vals = s->imp_own_v;
+        s->imp_own_k = s->imp_own_v = nullptr;
+        return VB_OK;
+    }
+    if (!g.rows && g.keys == s->gath_keys && s->gath_keys) {   // gather_maps already made owned SoA copies
+        s->lz_keys = s->gath_keys; s->lz_vals = s->gath_vals;
+        s->gath_keys = s->gath_vals = nullptr;
+        return VB_OK;
+    }
+    DevBuf k(c), v(c);
+    TRY(k.alloc(g.n * 8));
+    if (g.rows) {
+        TRY(v.alloc(g.n * 8));
+        KLaunch kl(s, K_MISC);
+        u64 blocks = std::min<u64>((g.n + 255) / 256, (u64)c->sm_count * 8);
+        aos_to_soa_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(g.rows, g.n, k.as<u64>(), v.as<u64>());
+        TRY(kl.done("aos_to_soa_kernel"));
+    } else {
+        CU(cudaMemcpyAsync(k.p, g.keys, g.n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (g.vals) { TRY(v.alloc(g.n * 8)); CU(cudaMemcpyAsync(v.p, g.vals, g.n * 8, cudaMemcpyDeviceToDevice, c->stream)); }
+    }
+    s->lz_keys = (u64 *)k.release();
+    s->lz_vals = (u64 *)v.release();
+    return VB_OK;
+}
+
+static void free_lazy_rows(vb_shuf *s)
+{
+    dev_free(s->ctx, s->lz_keys); dev_free(s->ctx, s->lz_vals);
+    s->lz_keys = s->lz_vals = nullptr;
+}
+
+// group everything (caller holds c->mu)
+static int ensure_grouped(vb_shuf *s)
+{
+    if (!s->lazy) return VB_OK;
+    Gathered g;
+    g.keys = s->lz_keys; g.vals = s->lz_vals; g.n = s->lz_n;
+    TRY(seal_group(s, g));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    free_lazy_rows(s);
+    s->lazy = false;
+    return VB_OK;
+}
+
+// match[i] = 1 iff keys[i] is in the dictionary; its slot is marked in slot_flag
+__global__ void semi_probe_kernel(const u64 *__restrict__ keys, u64 n, Table t, unsigned char *__restrict__ slot_flag, unsigned char *__restrict__ match)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 st = (u64)gridDim.x * blockDim.x;
+    const u64 pol = policy_evict_first();
+    for (; i < n; i += st) {
+        const u32 sl = table_find(t, ld_stream_u64(keys + i, pol));
+        const bool hit = sl != 0xFFFFFFFFu;
+        match[i] = hit ? 1 : 0;
+        if (hit) slot_flag[sl] = 1;
+    }
+}
+__global__ void mark_rows_kernel(const u32 *__restrict__ slot_of_row, u64 n, const unsigned char *__restrict__ slot_flag, unsigned char *__restrict__ match)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 st = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += st) match[i] = slot_flag[slot_of_row[i]];
+}
+
+// stable compaction, 4096 rows per block: counts, scan, scatter
+constexpr int CP_THREADS = 256, CP_ITEMS = 16, CP_TILE = CP_THREADS * CP_ITEMS;
+__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const unsigned char *__restrict__ match, u64 n, u64 *__restrict__ block_cnt)
+{
+    __shared__ u32 ws[CP_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * CP_TILE + (u64)threadIdx.x * CP_ITEMS;
+    u32 c = 0;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i) c += (base + i < n) ? match[base + i] : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { u32 t = 0; for (int w = 0; w < CP_THREADS / 32; ++w) t += ws[w]; block_cnt[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(CP_THREADS)
+compact_scatter_kernel(const unsigned char *__restrict__ match, u64 n, const u64 *__restrict__ block_off, const u64 *__restrict__ keys,
+                       const u64 *__restrict__ vals, u64 *__restrict__ out_keys, u64 *__restrict__ out_vals)
+{
+    __shared__ u32 ws[CP_THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 base = (u64)blockIdx.x * CP_TILE + (u64)tid * CP_ITEMS;
+    unsigned char m[CP_ITEMS];
+    u32 c = 0;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i) { m[i] = (base + i < n) ? match[base + i] : 0; c += m[i]; }
+    u32 incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (u32)off) incl += t; }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    u32 wbase = 0;
+    for (u32 w = 0; w < warp; ++w) wbase += ws[w];
+    u64 o = block_off[blockIdx.x] + wbase + incl - c;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i)
+        if (m[i]) { out_keys[o] = keys[base + i]; if (out_vals) out_vals[o] = vals ? vals[base + i] : 0ull; ++o; }
+}
+
+static int exclusive_scan_u64(vb_shuf *s, const u64 *in, u64 *out, u64 n, u64 *d_total);
+
+static int compact_rows(vb_shuf *s, const u64 *keys, const u64 *vals, u64 n, const unsigned char *match, DevBuf &ok, DevBuf &ov, u64 *m_out)
+{
+    vb_ctx *c = s->ctx;
+    *m_out = 0;
+    if (n == 0) return VB_OK;
+    const u64 blocks = (n + CP_TILE - 1) / CP_TILE;
+    DevBuf cnt(c), off(c), tot(c);
+    TRY(cnt.alloc(blocks * 8)); TRY(off.alloc(blocks * 8)); TRY(tot.alloc(8));
+    {
+        KLaunch kl(s, K_JOIN);
+        compact_count_kernel<<<(unsigned)blocks, CP_THREADS, 0, c->stream>>>(match, n, cnt.as<u64>());
+        TRY(kl.done("compact_count_kernel"));
+    }
+    TRY(exclusive_scan_u64(s, cnt.as<u64>(), off.as<u64>(), blocks, tot.as<u64>()));
+    u64 m = 0;
+    CU(cudaMemcpyAsync(c->h_scratch, tot.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    m = *(u64 *)c->h_scratch;
+    *m_out = m;
+    if (m == 0) return VB_OK;
+    TRY(ok.alloc(m * 8));
+    TRY(ov.alloc(m * 8));
+    KLaunch kl(s, K_JOIN);
+    compact_scatter_kernel<<<(unsigned)blocks, CP_THREADS, 0, c->stream>>>(match, n, off.as<u64>(), keys, vals, ok.as<u64>(), ov.as<u64>());
+    return kl.done("compact_scatter_kernel");
+}
+
+static vb_shuf *make_internal_like(const vb_shuf *s)
+{
+    vb_shuf *t = new vb_shuf();
+    t->ctx = s->ctx; t->id = s->id; t->n_map = 0; t->n_reduce = s->n_reduce;
+    t->kdt = s->kdt; t->vdt = s->vdt; t->agg = s->agg; t->part = s->part; t->key_width = s->key_width;
+    t->rank = 0; t->world = 1;                      // internal shuffles are device-local
+    t->sealed = true;
+    return t;
+}
+
+extern "C" int32_t vb_shuffle_free(vb_shuf *s);
+
+// both sides lazy: internal (left, right) shuffles grouped over the rows whose key occurs on both sides
+static int filtered_pair(vb_shuf *l, vb_shuf *r, vb_shuf **fl_out, vb_shuf **fr_out)
+{
+    auto it = l->filtered.find(r->uid);
+    if (it != l->filtered.end()) { *fl_out = it->second.first; *fr_out = it->second.second; return VB_OK; }
+    vb_ctx *c = l->ctx;
+    vb_shuf *fl = make_internal_like(l), *fr = make_internal_like(r);
+    auto fail = [&](int rc) { delete fl; delete fr; return rc; };
+    fl->bucket_off.assign((size_t)l->n_reduce + 1, 0); fl->val_off = fl->bucket_off;
+    fr->bucket_off = fl->bucket_off; fr->val_off = fl->bucket_off;
+    if (l->lz_n && r->lz_n) {
+        // 1. dictionary of the right keys (slot per right row)
+        DevBuf ids_r(c);
+        int rc = ids_r.alloc(r->lz_n * 4);
+        if (rc) return fail(rc);
+        std::vector<AggInput> in(1);
+        in[0] = AggInput{IN_SOA, r->lz_keys, nullptr, r->lz_n, VB_DEVICE};
+        void *tab = nullptr; u32 log_cap = 0; u64 n_ins = 0;
+        rc = build_table(l, K_DICT, in, OPK_DICT, TX_NONE, r->hint, &tab, &log_cap, &n_ins, ids_r.as<u32>());
+        if (rc) return fail(rc);
+        DevBuf tab_guard(c); tab_guard.p = tab;
+        const u64 cap = 1ull << log_cap;
+        // 2. probe with every left row; 3. mark the right rows whose key matched
+        DevBuf slot_flag(c), ml(c), mr(c);
+        if ((rc = slot_flag.alloc(cap + 1 + 16)) || (rc = ml.alloc(l->lz_n)) || (rc = mr.alloc(r->lz_n))) return fail(rc);
+        cudaMemsetAsync(slot_flag.p, 0, cap + 1 + 16, c->stream);
+        {
+            KLaunch kl(l, K_JOIN);
+            const unsigned g = (unsigned)std::min<u64>((l->lz_n + 255) / 256, (u64)c->sm_count * 16);
+            semi_probe_kernel<<<g, 256, 0, c->stream>>>(l->lz_keys, l->lz_n, table_at(tab, log_cap), slot_flag.as<unsigned char>(), ml.as<unsigned char>());
+            if ((rc = kl.done("semi_probe_kernel"))) return fail(rc);
+        }
+        {
+            KLaunch kl(l, K_JOIN);
+            const unsigned g = (unsigned)std::min<u64>((r->lz_n + 255) / 256, (u64)c->sm_count * 16);
+            mark_rows_kernel<<<g, 256, 0, c->stream>>>(ids_r.as<u32>(), r->lz_n, slot_flag.as<unsigned char>(), mr.as<unsigned char>());
+            if ((rc = kl.done("mark_rows_kernel"))) return fail(rc);
+        }
+        // 4. stable compaction of both sides, then the ordinary cogroup of what is left
+        DevBuf lk(c), lv(c), rk(c), rv(c);
+        u64 m_l = 0, m_r = 0;
+        if ((rc = compact_rows(l, l->lz_keys, l->lz_vals, l->lz_n, ml.as<unsigned char>(), lk, lv, &m_l))) return fail(rc);
+        if ((rc = compact_rows(l, r->lz_keys, r->lz_vals, r->lz_n, mr.as<unsigned char>(), rk, rv, &m_r))) return fail(rc);
+        if (m_l && m_r) {
+            Gathered gl, gr;
+            gl.keys = lk.as<u64>(); gl.vals = lv.as<u64>(); gl.n = m_l;
+            gr.keys = rk.as<u64>(); gr.vals = rv.as<u64>(); gr.n = m_r;
+            if ((rc = seal_group(fl, gl)) || (rc = seal_group(fr, gr))) {
+                l->trash.push_back(fl); l->trash.push_back(fr);      // freed with l (vb_shuffle_free would re-lock the context here)
+                return rc;
+            }
+            // kernel counters of the internal shuffles belong to the caller's statistics
+            for (int k = 0; k < K_N; ++k) { l->klaunch[k] += fl->klaunch[k] + fr->klaunch[k]; }
+            l->st.kernel_launches += fl->st.kernel_launches + fr->st.kernel_launches;
+            l->st.table_slots = std::max<u64>(l->st.table_slots, std::max<u64>(cap, std::max(fl->st.table_slots, fr->st.table_slots)));
+        }
+        cudaStreamSynchronize(c->stream);
+    }
+    l->filtered[r->uid] = std::make_pair(fl, fr);
+    *fl_out = fl; *fr_out = fr;
     return VB_OK;
 }
 
@@ -2261,7 +2735,9 @@ extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
                 } else {
                     Gathered g;
                     TRY(gather_maps(s, &g));
-                    if (s->agg == VB_AGG_SORT) TRY(seal_sort(s, g)); else TRY(seal_group(s, g));
+                    if (s->agg == VB_AGG_SORT) TRY(seal_sort(s, g));
+                    else if (s->agg == VB_AGG_COGROUP && lazy_cogroup_enabled()) TRY(seal_lazy(s, g, false));
+                    else TRY(seal_group(s, g));
                 }
             } else {
                 if (!s->exported || !s->imported) return set_err(VB_ERR_STATE, "world > 1: seal needs export_prepare + import");
@@ -2274,10 +2750,18 @@ extern "C" int32_t vb_shuffle_seal(vb_shuf *s)
                     }
                     DevBuf guard(c); guard.p = tab;
                     TRY(finalize_reduce(s, tab, log_cap, n_ins));
+                } else if (s->agg == VB_AGG_SORT) {
+                    if (s->sort_part_rows.size() != s->n_reduce) return set_err(VB_ERR_STATE, "multi-rank sort_by_key goes through vb_shuffle_exchange");
+                    Gathered g;
+                    g.keys = s->imp_keys; g.vals = s->imp_vals; g.n = s->imp_n;
+                    TRY(seal_sort(s, g));        // the received runs are key-range disjoint per partition: one stable sort orders them all
+                    s->bucket_off.assign((size_t)s->n_reduce + 1, 0);
+                    for (u32 p = 0; p < s->n_reduce; ++p) s->bucket_off[p + 1] = s->bucket_off[p] + s->sort_part_rows[p];
                 } else {
                     Gathered g;
                     g.keys = s->imp_keys; g.vals = s->imp_vals; g.n = s->imp_n;
-                    TRY(seal_group(s, g));
+                    if (s->agg == VB_AGG_COGROUP && lazy_cogroup_enabled()) TRY(seal_lazy(s, g, s->imp_keys == s->imp_own_k && s->imp_own_k));
+                    else TRY(seal_group(s, g));
                 }
             }
             release_inputs(s);
@@ -2315,6 +2799,11 @@ extern "C" int32_t vb_shuffle_reduce_size(vb_shuf *s, uint32_t r, uint64_t *n_ke
     if (!s) return set_err(VB_ERR_INVALID, "NULL shuffle");
     if (r >= s->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", r, s->n_reduce);
     TRY(wait_sealed(s));
+    if (s->lazy) {                                   // first cogroup materialisation: group all rows now
+        std::lock_guard<std::mutex> lk(s->ctx->mu);
+        CU(cudaSetDevice(s->ctx->device));
+        TRY(ensure_grouped(s));
+    }
     if (n_keys) *n_keys = s->bucket_off[r + 1] - s->bucket_off[r];
     if (n_vals) *n_vals = is_group_op(s->agg) ? s->val_off[r + 1] - s->val_off[r] : 0;
     return VB_OK;
@@ -2339,6 +2828,7 @@ extern "C" int32_t vb_shuffle_reduce(vb_shuf *s, uint32_t r, void *out_keys, voi
     vb_ctx *c = s->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    TRY(ensure_grouped(s));
     const u64 b0 = s->bucket_off[r], nk = s->bucket_off[r + 1] - b0;
     TRY(copy_out(s, out_keys, s->res_keys ? s->res_keys + b0 : nullptr, nk * 8, dst_loc));
     if (is_group_op(s->agg)) {
@@ -2380,6 +2870,11 @@ extern "C" int32_t vb_shuffle_reduce_blob_size(vb_shuf *s, uint32_t r, uint64_t 
     if (!s || !n_bytes) return set_err(VB_ERR_INVALID, "NULL argument");
     if (r >= s->n_reduce) return set_err(VB_ERR_INVALID, "reduce_id %u >= n_reduce %u", r, s->n_reduce);
     TRY(wait_sealed(s));
+    if (s->lazy) {
+        std::lock_guard<std::mutex> lk(s->ctx->mu);
+        CU(cudaSetDevice(s->ctx->device));
+        TRY(ensure_grouped(s));
+    }
     *n_bytes = blob_bytes(s, r);
     return VB_OK;
 }
@@ -2393,6 +2888,7 @@ extern "C" int32_t vb_shuffle_reduce_blob(vb_shuf *s, uint32_t r, void *out_blob
     vb_ctx *c = s->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    TRY(ensure_grouped(s));
     const u64 bytes = blob_bytes(s, r);
     const u64 b0 = s->bucket_off[r], nk = s->bucket_off[r + 1] - b0;
     DevBuf tmp(c);
@@ -2527,12 +3023,27 @@ static int join_plan(vb_shuf *l, vb_shuf *r, u32 rid, JoinPlan **out)
     return VB_OK;
 }
 
+// the pair of shuffles whose CSR the join reads: the filtered internal pair while both sides are still lazy
+static int join_sides(vb_shuf *&l, vb_shuf *&r)
+{
+    if (l->lazy && r->lazy && l != r) {
+        vb_shuf *fl = nullptr, *fr = nullptr;
+        TRY(filtered_pair(l, r, &fl, &fr));
+        l = fl; r = fr;
+        return VB_OK;
+    }
+    TRY(ensure_grouped(l));
+    TRY(ensure_grouped(r));
+    return VB_OK;
+}
+
 extern "C" int32_t vb_join_size(vb_shuf *l, vb_shuf *r, uint32_t rid, uint64_t *n_out)
 {
     TRY(join_check(l, r, rid));
     if (!n_out) return set_err(VB_ERR_INVALID, "n_out is NULL");
     std::lock_guard<std::mutex> lk(l->ctx->mu);
     CU(cudaSetDevice(l->ctx->device));
+    TRY(join_sides(l, r));
     JoinPlan *p = nullptr;
     TRY(join_plan(l, r, rid, &p));
     *n_out = p->total;
@@ -2546,6 +3057,7 @@ extern "C" int32_t vb_join(vb_shuf *l, vb_shuf *r, uint32_t rid, void *out_k, vo
     vb_ctx *c = l->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    TRY(join_sides(l, r));
     JoinPlan *p = nullptr;
     TRY(join_plan(l, r, rid, &p));
     const u64 total = p->total;
@@ -2601,8 +3113,11 @@ extern "C" int32_t vb_shuffle_free(vb_shuf *s)
         dev_free(c, s->res_keys); dev_free(c, s->res_comb); dev_free(c, s->res_offs); dev_free(c, s->res_vals);
         dev_free(c, s->dict); dev_free(c, s->dense_of_slot);
         for (auto &kv : s->join_plans) { dev_free(c, kv.second.pos); dev_free(c, kv.second.match); }
+        free_lazy_rows(s);
         cudaStreamSynchronize(c->stream);
     }
+    for (auto &kv : s->filtered) { vb_shuffle_free(kv.second.first); vb_shuffle_free(kv.second.second); }
+    for (vb_shuf *t : s->trash) vb_shuffle_free(t);
     delete s;
     return VB_OK;
 }
@@ -2659,6 +3174,39 @@ extern "C" uint64_t vb_slice(uint64_t n, uint64_t num_slices, uint64_t *starts)
     for (uint64_t i = 0; i < n; ++i) starts[i + 1] = i;
     starts[n + 1] = n;
     return n + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident sources
+// ---------------------------------------------------------------------------------------------
+__global__ void range_kernel(u64 *__restrict__ out, u64 start, u64 step, u64 n)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 st = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += st) out[i] = start + i * step;
+}
+
+// Context::range (src/context.rs:419-431): the elements of (start..=end).step_by(step), written on the device.
+extern "C" uint64_t vb_range_len(uint64_t start, uint64_t end, uint64_t step)
+{
+    if (step == 0 || end < start) return 0;
+    return (end - start) / step + 1;
+}
+
+extern "C" int32_t vb_range(vb_ctx *c, void *out_dev, uint64_t start, uint64_t end, uint64_t step)
+{
+    if (!c) return set_err(VB_ERR_INVALID, "ctx is NULL");
+    if (step == 0) return set_err(VB_ERR_INVALID, "step must be >= 1 (Rust's step_by panics on 0)");
+    const u64 n = vb_range_len(start, end, step);
+    if (n == 0) return VB_OK;
+    if (!out_dev) return set_err(VB_ERR_INVALID, "out_dev is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 16);
+    range_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((u64 *)out_dev, start, step, n);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return VB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

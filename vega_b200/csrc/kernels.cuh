@@ -53,6 +53,38 @@ enum : int { OPK_ADD_U64 = 0, OPK_ADD_F64 = 1, OPK_MIN_U64 = 2, OPK_MAX_U64 = 3,
 
 VB_HD u64 op_identity(int opk) { return opk == OPK_MIN_U64 ? ~0ull : 0ull; }
 
+// Table accesses can carry an L2 evict_last hint (the stream is evict_first): A/B-measured, see VB_TABLE_EVICT_LAST.
+#ifndef VB_TABLE_EVICT_LAST
+#define VB_TABLE_EVICT_LAST 0
+#endif
+VB_D u64 table_policy()
+{
+#if VB_TABLE_EVICT_LAST
+    return policy_evict_last();
+#else
+    return 0;
+#endif
+}
+
+template <int OPK>
+VB_D void op_red_hint(u64 *acc, u64 v, u64 pol)
+{
+#if VB_TABLE_EVICT_LAST
+    if (OPK == OPK_ADD_U64) asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(acc), "l"(v), "l"(pol) : "memory");
+    else if (OPK == OPK_COUNT) asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(acc), "l"(1ull), "l"(pol) : "memory");
+    else if (OPK == OPK_ADD_F64) asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(acc), "d"(__longlong_as_double((long long)v)), "l"(pol) : "memory");
+    else if (OPK == OPK_MIN_U64) asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(acc), "l"(v), "l"(pol) : "memory");
+    else if (OPK == OPK_MAX_U64) asm volatile("red.global.max.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(acc), "l"(v), "l"(pol) : "memory");
+#else
+    (void)pol;
+    if (OPK == OPK_ADD_U64) atomicAdd((unsigned long long *)acc, (unsigned long long)v);
+    else if (OPK == OPK_COUNT) atomicAdd((unsigned long long *)acc, 1ull);
+    else if (OPK == OPK_ADD_F64) atomicAdd((double *)acc, __longlong_as_double((long long)v));
+    else if (OPK == OPK_MIN_U64) atomicMin((unsigned long long *)acc, (unsigned long long)v);
+    else if (OPK == OPK_MAX_U64) atomicMax((unsigned long long *)acc, (unsigned long long)v);
+#endif
+}
+
 template <int OPK>
 VB_D void op_red(u64 *acc, u64 v)
 {
@@ -84,6 +116,19 @@ VB_D Bucket4 ld_bucket(const u64 *p)
                  : "=l"(b.k0), "=l"(b.k1), "=l"(b.k2), "=l"(b.k3)
                  : "l"(p));
     return b;
+}
+VB_D Bucket4 ld_bucket_hint(const u64 *p, u64 pol)
+{
+#if VB_TABLE_EVICT_LAST
+    Bucket4 b;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=l"(b.k0), "=l"(b.k1), "=l"(b.k2), "=l"(b.k3)
+                 : "l"(p), "l"(pol));
+    return b;
+#else
+    (void)pol;
+    return ld_bucket(p);
+#endif
 }
 VB_D int bucket_find(const Bucket4 &b, u64 key)
 {
@@ -178,6 +223,7 @@ VB_D void ha_process_rows(const Table &t, TableCtl *ctl, u64 (&k)[ROWS], u64 (&v
                           u32 *__restrict__ slot_out, u64 *hc_keys, u64 *hc_acc, bool use_cache, u32 &my_inserts, u32 &my_hits)
 {
     const u64 cap = 1ull << t.log_cap;
+    const u64 tpol = table_policy();
     const u32 hshift = 64 - (t.log_cap - 2);
     u64 h[ROWS];
 #pragma unroll
@@ -208,7 +254,7 @@ VB_D void ha_process_rows(const Table &t, TableCtl *ctl, u64 (&k)[ROWS], u64 (&v
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
         bidx[j] = h[j] >> hshift;
-        if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
+        if (ok[j]) bk[j] = ld_bucket_hint(&t.keys[4 * bidx[j]], tpol);
     }
     bool pending = true;
 #pragma unroll 1
@@ -231,7 +277,7 @@ VB_D void ha_process_rows(const Table &t, TableCtl *ctl, u64 (&k)[ROWS], u64 (&v
             }
             if (hit >= 0) {
                 const u64 sl = 4 * bidx[j] + (u64)hit;
-                op_red<OPK>(&t.accs[sl], v[j]);
+                op_red_hint<OPK>(&t.accs[sl], v[j], tpol);
                 if (OPK == OPK_DICT) st_stream_u32(slot_out + row0 + (u64)j * HA_THREADS, (u32)sl);
                 ok[j] = false;
             } else {
@@ -241,7 +287,7 @@ VB_D void ha_process_rows(const Table &t, TableCtl *ctl, u64 (&k)[ROWS], u64 (&v
         if (pending) {
 #pragma unroll
             for (int j = 0; j < ROWS; ++j)
-                if (ok[j]) bk[j] = ld_bucket(&t.keys[4 * bidx[j]]);
+                if (ok[j]) bk[j] = ld_bucket_hint(&t.keys[4 * bidx[j]], tpol);
         }
     }
     if (pending) atomicExch(&ctl->abort, 1u);   // probe chain longer than HA_MAX_PROBE buckets

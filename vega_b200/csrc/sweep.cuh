@@ -6,8 +6,8 @@
 //   * tiles are claimed in order from an atomic counter and chained with a decoupled look-back
 //     (per (tile, digit) status words), so there is no per-part histogram kernel and no scan kernel per pass —
 //     the only other kernel is ONE histogram pass that counts every digit position of the key at once;
-//   * 3 CTA barriers per tile (the old rp_scatter_kernel had 5): warp-private u16 counters are cleared by their
-//     own warp, the staging buffer is only rewritten after the next tile's first barrier.
+//   * 4 CTA barriers per tile (the old rp_scatter_kernel had 5): warp-private u16 counters are cleared by their
+//     own warp, the staging buffer is only rewritten after the next tile's third barrier.
 //
 // Stable: rows keep their input order inside every digit (tile order → warp order → lane-striped item order),
 // which the LSD sort and the group value order (tests/test_pair_rdd.rs:30-36) rely on.
@@ -21,6 +21,10 @@ constexpr int SW_THREADS = 512;
 constexpr int SW_WARPS = SW_THREADS / 32;
 constexpr int SW_NB = 256;
 constexpr u32 SW_FLAG_AGG = 1u << 30, SW_FLAG_INC = 2u << 30, SW_VAL_MASK = (1u << 30) - 1;   // look-back words
+#ifndef VB_SW_LB
+#define VB_SW_LB 16
+#endif
+constexpr int SW_LB = VB_SW_LB;            // look-back window: status words fetched per step
 constexpr u64 SW_MAX_ROWS = 1ull << 30;     // prefixes live in 30 bits; larger inputs use the rp_* kernels
 
 // items per thread by row width: both tile buffers (raw + staged) of 2 resident CTAs fit the 227 KB of an SM
@@ -232,6 +236,9 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
         for (int i = 0; i < K; ++i) {
             const u32 d = dr[i];
             u32 peers;
+#ifdef VB_SW_DEBUG_NORANK        // timing bisection only
+            if (full) { peers = 1u << lane; } else
+#endif
             if (full) {
                 peers = 0xffffffffu;
 #pragma unroll
@@ -279,22 +286,7 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
             for (u32 w = 0; w < warp; ++w) excl_local += wtot[w];
             dbase[tid] = excl_local;
         }
-        // every thread stages its items (warp offsets are in cnt, digit starts in dbase — dbase of OTHER digits is
-        // needed, so staging waits for one more barrier; the look-back below runs in its shadow)
-        if (tid < SW_NB) {
-            u32 prefix = 0;
-            if (tile > 0) {
-                for (u32 tt = tile; tt-- > 0;) {
-                    u32 v;
-                    do { v = ld_relaxed_u32(&a.state[(size_t)tt * SW_NB + tid]); } while ((v >> 30) == 0u);
-                    prefix += v & SW_VAL_MASK;
-                    if (v & SW_FLAG_INC) break;
-                }
-                st_relaxed_u32(&a.state[(size_t)tile * SW_NB + tid], SW_FLAG_INC | (prefix + total));
-            }
-            gbase[tid] = a.digit_base[tid] + prefix - excl_local;
-        }
-        __syncthreads();                                                        // B3: dbase / gbase visible
+        __syncthreads();                                                        // B3: dbase visible
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             const u32 d = dr[i] & 0xFFFFu;
@@ -305,10 +297,51 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
                 st_dig[pos] = (unsigned char)d;
             }
         }
+        // ---- 4. decoupled look-back, thread d < 256 for digit d.  It runs AFTER staging: the tile's registers are
+        // dead (room for a window of SW_LB status words in flight per thread) and the predecessors have had the whole
+        // staging phase to publish.  A serial one-tile-per-L2-round-trip walk cannot keep up with > 10 tiles/us
+        // chip-wide (measured: 3x slower than the two-kernel pass), so SW_LB predecessors are fetched per step.
+        if (tid < SW_NB) {
+            u32 prefix = 0;
+#ifdef VB_SW_DEBUG_NOLB          // timing bisection only: results are wrong
+            if (false) {
+#else
+            if (tile > 0) {
+#endif
+                long long tt = (long long)tile - 1;
+                bool done = false;
+                while (!done) {
+                    u32 v[SW_LB];
+#pragma unroll
+                    for (int j = 0; j < SW_LB; ++j) {
+                        const long long idx = tt - j;
+                        v[j] = idx >= 0 ? ld_relaxed_u32(&a.state[(size_t)idx * SW_NB + tid]) : SW_FLAG_INC;   // before tile 0: prefix 0
+                    }
+                    int used = 0;
+#pragma unroll
+                    for (int j = 0; j < SW_LB; ++j) {
+                        if (!done && used == j) {                 // stop consuming at the first word not yet published
+                            const u32 x = v[j];
+                            if ((x >> 30) != 0u) {
+                                prefix += x & SW_VAL_MASK;
+                                ++used;
+                                if (x & SW_FLAG_INC) done = true;
+                            }
+                        }
+                    }
+                    tt -= used;
+                }
+                st_relaxed_u32(&a.state[(size_t)tile * SW_NB + tid], SW_FLAG_INC | (prefix + total));
+            }
+            gbase[tid] = a.digit_base[tid] + prefix - excl_local;
+        }
         __syncthreads();                                                        // B4: tile staged
         for (u32 i = lane; i < SW_NB / 2; i += 32) ((u32 *)my_cnt)[i] = 0;      // own counters: next tile's ranking
         __syncwarp();
         KeyT *ok = (KeyT *)a.out_keys;
+#ifdef VB_SW_DEBUG_NOWRITE       // timing bisection only
+        if (tile == 0xFFFFFFFEu)
+#endif
         for (u32 p = tid; p < rows_here; p += SW_THREADS) {
             const u32 o = gbase[st_dig[p]] + p;
             ok[o] = st_keys[p];

@@ -152,6 +152,19 @@ class Context:
 
     make_rdd = parallelize
 
+    def range(self, start, end, step, num_slices):
+        """`sc.range(start, end, step, num_slices)` (src/context.rs:419-431): (start..=end).step_by(step), generated
+        ON the device (vb_range) — a source RDD with no host array and no H2D copy."""
+        import torch
+        n = self._lib.vb_range_len(start, end, step)
+        dev = f"cuda:{self._lib.vb_ctx_device(self._h)}"
+        t = torch.empty(n, dtype=torch.int64, device=dev)
+        torch.cuda.current_stream(t.device).synchronize()
+        L.check(self._lib.vb_range(self._h, ctypes.c_void_p(t.data_ptr()) if n else None, start, end, step))
+        col = _Col(t)
+        col.code = L.VB_U64
+        return Rdd(self, col, num_slices)
+
     def gen_pairs(self, out_rows=None, out_keys=None, out_vals=None, first=0, n=0, mode="uniform", n_distinct=1,
                   rank_base=0, seed_k=1, seed_v=2, zipf_s=0.0):
         """Fill device buffers (torch CUDA tensors) with the synthetic workload of SURVEY.md §8(d)."""
