@@ -202,6 +202,9 @@ typedef struct vb_xstats {
     double exchange_ms;     /* device time of the exchange (profiling on): NCCL group, or counts+scatter+barrier for P2P */
     int32_t kind;           /* vb_xchg actually used */
     int32_t pad;
+    double prepare_wall_ms; /* host wall clock: finish the map side + pack by destination (merge, multisplit, their syncs) */
+    double counts_wall_ms;  /* host wall clock: count all-gather + D2H */
+    double post_wall_ms;    /* host wall clock: buffers + enqueueing the grouped send/recv (or handles + scatter + barrier) */
 } vb_xstats;
 VB_API int32_t vb_comm_unique_id(void *id_out /*VB_UNIQUE_ID_BYTES*/);
 VB_API int32_t vb_ctx_comm_init(vb_ctx *ctx, const void *unique_id, uint32_t rank, uint32_t world);

@@ -40,7 +40,8 @@ class vb_stats(ctypes.Structure):
 
 class vb_xstats(ctypes.Structure):
     _fields_ = [("sent_rows", ctypes.c_uint64), ("recv_rows", ctypes.c_uint64), ("exchanges", ctypes.c_uint64),
-                ("exchange_ms", ctypes.c_double), ("kind", ctypes.c_int32), ("pad", ctypes.c_int32)]
+                ("exchange_ms", ctypes.c_double), ("kind", ctypes.c_int32), ("pad", ctypes.c_int32),
+                ("prepare_wall_ms", ctypes.c_double), ("counts_wall_ms", ctypes.c_double), ("post_wall_ms", ctypes.c_double)]
 
 
 # name -> (restype, argtypes); also the list of symbols include/vega_b200.h declares

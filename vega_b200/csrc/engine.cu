@@ -7,6 +7,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -404,6 +405,7 @@ static void resolve_timers(vb_shuf *s)
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
             if (t.klass >= 0) s->kms[t.klass] += ms;
             else if (t.klass == -1) s->st.map_ms += ms;
+            else if (t.klass == -3) s->xst.exchange_ms += ms;
             else s->st.seal_ms += ms;
             int hot = is_reduce_op(s->agg) ? K_HASH_AGG : K_RP_SCATTER;
             if (t.klass == hot) {
@@ -885,10 +887,15 @@ static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist,
     return false;
 }
 
+// The one-kernel pass is OPT-IN (VEGA_B200_SWEEP=1).  Measured on B200 (profiles/r2_sweep_bisection.jsonl,
+// profiles/r2_ncu_sweep.txt): without its look-back it is 15 % faster than rp_scatter_kernel (7.6 vs 8.9 ms per
+// 1e9-row pass of (u32,u64) rows), but at ~22 tiles/us chip-wide the decoupled look-back needs ~40 predecessors per
+// tile (three windows of 16 status words, each an L2 round trip spent behind a barrier) and costs 3.3 ms per pass,
+// which lands the pass at 10.9 ms — on par with histogram + scan + scatter (10.2 ms), not ahead of it.
 static bool sweep_enabled()
 {
-    static const bool off = getenv("VEGA_B200_NO_SWEEP") != nullptr;
-    return !off;
+    static const bool on = getenv("VEGA_B200_SWEEP") != nullptr && getenv("VEGA_B200_NO_SWEEP") == nullptr;
+    return on;
 }
 
 // rows of `ld` must be a plain row stream (every row valid) with 16-byte aligned column bases
@@ -1017,6 +1024,39 @@ __global__ void bucket_hist_kernel(const u64 *__restrict__ keys, u64 n, Digit dg
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&cnt[get_partition(keys[i], dg.key_width, dg.fm)], 1u);
+}
+
+// Unordered multisplit of a combined table's occupied slots (reduce ops only; <= 256 bins): see kernels.cuh.
+static int multisplit_table_unordered(vb_shuf *s, const Table &t, int mode, u32 nbins, u64 *out_keys, u64 *out_vals, std::vector<u64> &bin_off)
+{
+    vb_ctx *c = s->ctx;
+    bin_off.assign((size_t)nbins + 1, 0);
+    const u64 cap = 1ull << t.log_cap;
+    DevBuf cc(c);
+    TRY(cc.alloc(2 * TS_MAX_BINS * 4));
+    CU(cudaMemsetAsync(cc.p, 0, 2 * TS_MAX_BINS * 4, c->stream));
+    u32 *counts = cc.as<u32>(), *cursors = cc.as<u32>() + TS_MAX_BINS;
+    Digit dg = make_bucket_digit(s, mode, 0, 0xFFFFFFFFu);
+    const unsigned grid = (unsigned)std::min<u64>((cap + TS_TILE) / TS_TILE, (u64)c->sm_count * 4);
+    {
+        KLaunch kl(s, K_RP_HIST, cap + 1);
+        if (mode == DG_DEST) table_bin_count_kernel<DG_DEST><<<grid, TS_THREADS, 0, c->stream>>>(t.keys, cap, dg, counts);
+        else table_bin_count_kernel<DG_BUCKET><<<grid, TS_THREADS, 0, c->stream>>>(t.keys, cap, dg, counts);
+        TRY(kl.done("table_bin_count_kernel"));
+    }
+    {
+        KLaunch kl(s, K_RP_SCATTER, cap + 1);
+        if (mode == DG_DEST) table_bin_scatter_kernel<DG_DEST><<<grid, TS_THREADS, 0, c->stream>>>(t.keys, t.accs, cap, dg, counts, cursors, out_keys, out_vals);
+        else table_bin_scatter_kernel<DG_BUCKET><<<grid, TS_THREADS, 0, c->stream>>>(t.keys, t.accs, cap, dg, counts, cursors, out_keys, out_vals);
+        TRY(kl.done("table_bin_scatter_kernel"));
+    }
+    u32 *h = (u32 *)c->h_scratch;
+    CU(cudaMemcpyAsync(h, counts, TS_MAX_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    u64 run = 0;
+    for (u32 d = 0; d < nbins; ++d) { bin_off[d] = run; run += h[d]; }
+    bin_off[nbins] = run;
+    return VB_OK;
 }
 
 // Stable multisplit of `n` loader rows by reduce partition (DG_BUCKET, nbins = n_reduce) or by
@@ -1575,7 +1615,9 @@ static int finalize_reduce(vb_shuf *s, void *tab, u32 log_cap, u64 n_ins)
     TRY(v.alloc(max_d * 8));
     const Table ft = table_at(tab, log_cap);
     Loader lt{LD_TABLE_KV, ft.keys, ft.accs, cap};
-    TRY(multisplit(s, lt, cap + 1, DG_BUCKET, R, max_d, k.as<u64>(), v.as<u64>(), s->bucket_off));
+    static const bool ordered_only = getenv("VEGA_B200_STABLE_TABLE_SPLIT") != nullptr;     // A/B switch
+    if (R <= (u32)TS_MAX_BINS && !ordered_only) TRY(multisplit_table_unordered(s, ft, DG_BUCKET, R, k.as<u64>(), v.as<u64>(), s->bucket_off));
+    else TRY(multisplit(s, lt, cap + 1, DG_BUCKET, R, max_d, k.as<u64>(), v.as<u64>(), s->bucket_off));
     const u64 D = s->bucket_off[R];
     const int tx = val_tx(s);
     if (tx != TX_NONE && D) {
@@ -1743,7 +1785,9 @@ static int export_prepare_locked(vb_shuf *s, uint64_t *counts)
             TRY(v.alloc((n_ins + 1) * 8));
             const Table et = table_at(tab, log_cap);
             Loader lt{LD_TABLE_KV, et.keys, et.accs, 1ull << log_cap};
-            TRY(multisplit(s, lt, (1ull << log_cap) + 1, DG_DEST, s->world, n_ins + 1, k.as<u64>(), v.as<u64>(), off));
+            static const bool ordered_only = getenv("VEGA_B200_STABLE_TABLE_SPLIT") != nullptr;
+            if (s->world <= (u32)TS_MAX_BINS && !ordered_only) TRY(multisplit_table_unordered(s, et, DG_DEST, s->world, k.as<u64>(), v.as<u64>(), off));
+            else TRY(multisplit(s, lt, (1ull << log_cap) + 1, DG_DEST, s->world, n_ins + 1, k.as<u64>(), v.as<u64>(), off));
             s->exp_keys = (u64 *)k.release();
             s->exp_vals = (u64 *)v.release();
         }
@@ -2161,9 +2205,16 @@ static int exchange_nccl_locked(vb_shuf *s)
     Comm *m = c->comm;
     const u32 W = m->world, me = m->rank;
     std::vector<u64> counts(W, 0);
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    auto t0 = now();
     TRY(export_prepare_locked(s, counts.data()));
+    s->xst.prepare_wall_ms += ms_since(t0);
+    t0 = now();
     const u64 *mat = nullptr;
     TRY(comm_gather_counts(c, counts.data(), &mat));
+    s->xst.counts_wall_ms += ms_since(t0);
+    t0 = now();
     std::vector<u64> rcnt(W), soff(W + 1, 0), roff(W + 1, 0);
     for (u32 p = 0; p < W; ++p) {
         rcnt[p] = mat[(size_t)p * (W + 2) + me];
@@ -2189,14 +2240,11 @@ static int exchange_nccl_locked(vb_shuf *s)
         }
     }
     NC(g_nccl.GroupEnd());
-    if (e0) {
+    if (e0) {       // resolved later (vb_shuffle_exchange_stats / vb_shuffle_stats): no host wait here
         cudaEventRecord(e1, c->stream);
-        cudaEventSynchronize(e1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        s->xst.exchange_ms += ms;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        s->timers.push_back(Timer{e0, e1, -3, 0});
     }
+    s->xst.post_wall_ms += ms_since(t0);
     s->xst.sent_rows += soff[W] - counts[me];
     s->xst.recv_rows += n_recv - rcnt[me];
     s->xst.exchanges += 1;
@@ -2459,6 +2507,9 @@ extern "C" int32_t vb_shuffle_exchange(vb_shuf *s, int32_t mode)
 extern "C" int32_t vb_shuffle_exchange_stats(vb_shuf *s, vb_xstats *out)
 {
     if (!s || !out) return set_err(VB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    cudaSetDevice(s->ctx->device);
+    resolve_timers(s);
     *out = s->xst;
     return VB_OK;
 }

@@ -958,6 +958,90 @@ template <typename KeyT, bool HAS_VAL, int BITS>
 constexpr size_t rp_scatter_smem() { return (size_t)RP_TILE * ((HAS_VAL ? 8 : 0) + sizeof(KeyT) + ((sizeof(KeyT) == 8 && HAS_VAL) ? 1 : 4)); }
 
 // ---------------------------------------------------------------------------------------------
+// Unordered multisplit of the occupied slots of a combined table (reduce ops): (key, combiner) rows by reduce
+// partition or by owner rank.  The reference's order inside a reduce partition is HashMap order (unspecified), so
+// no stability is needed here: two small kernels (count, scatter with one global cursor claim per tile and bin)
+// replace the histogram + single-CTA scan + stable scatter of the general pass, whose fixed cost (~150 us) is
+// most of a step's seal/exchange time once the map-side combine has shrunk 1e9 rows to 1e6.
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_THREADS = 256, TS_ITEMS = 8, TS_TILE = TS_THREADS * TS_ITEMS, TS_MAX_BINS = 256;
+
+template <int DGM>
+VB_D bool ts_load(const u64 *__restrict__ keys, u64 cap, u64 i, const Digit &dg, u64 &key, u32 &bin)
+{
+    if (i > cap) return false;
+    const u64 k = keys[i];
+    if (i == cap) { if (k != 1ull) return false; key = EMPTY_KEY; }      // special slot: a real key equal to the empty marker
+    else { if (k == EMPTY_KEY) return false; key = k; }
+    bin = rp_digit<u64, DGM>(dg, key);
+    return true;
+}
+
+template <int DGM>
+__global__ void __launch_bounds__(TS_THREADS) table_bin_count_kernel(const u64 *__restrict__ keys, u64 cap, Digit dg, u32 *__restrict__ counts)
+{
+    __shared__ u32 h[TS_MAX_BINS];
+    for (u32 d = threadIdx.x; d < TS_MAX_BINS; d += TS_THREADS) h[d] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * TS_THREADS;
+    for (u64 i = (u64)blockIdx.x * TS_THREADS + threadIdx.x; i <= cap; i += stride) {
+        u64 key; u32 bin;
+        if (ts_load<DGM>(keys, cap, i, dg, key, bin)) atomicAdd(&h[bin], 1u);
+    }
+    __syncthreads();
+    for (u32 d = threadIdx.x; d < TS_MAX_BINS; d += TS_THREADS) if (h[d]) atomicAdd(&counts[d], h[d]);
+}
+
+template <int DGM>
+__global__ void __launch_bounds__(TS_THREADS)
+table_bin_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ accs, u64 cap, Digit dg, const u32 *__restrict__ counts,
+                         u32 *__restrict__ cursors, u64 *__restrict__ out_keys, u64 *__restrict__ out_vals)
+{
+    __shared__ u32 base[TS_MAX_BINS], tile_cnt[TS_MAX_BINS], tile_base[TS_MAX_BINS], ws[TS_THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    {   // exclusive scan of the global counts (every CTA redoes these 256 adds instead of a separate scan kernel)
+        const u32 c = counts[tid];
+        u32 incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (u32)off) incl += t; }
+        if (lane == 31) ws[warp] = incl;
+        __syncthreads();
+        u32 b = 0;
+        for (u32 w = 0; w < warp; ++w) b += ws[w];
+        base[tid] = b + incl - c;
+        tile_cnt[tid] = 0;
+    }
+    __syncthreads();
+    const u64 n_tiles = (cap + 1 + TS_TILE - 1) / TS_TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        u64 key[TS_ITEMS], val[TS_ITEMS];
+        u32 br[TS_ITEMS];                         // bin | local rank << 8 ; 0xFFFFFFFF = no row
+#pragma unroll
+        for (int j = 0; j < TS_ITEMS; ++j) {
+            const u64 i = tile * TS_TILE + (u64)j * TS_THREADS + tid;
+            u32 bin;
+            br[j] = 0xFFFFFFFFu;
+            if (ts_load<DGM>(keys, cap, i, dg, key[j], bin)) {
+                val[j] = accs[i];
+                br[j] = bin | (atomicAdd(&tile_cnt[bin], 1u) << 8);
+            }
+        }
+        __syncthreads();
+        { const u32 c = tile_cnt[tid]; if (c) tile_base[tid] = base[tid] + atomicAdd(&cursors[tid], c); }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < TS_ITEMS; ++j) {
+            if (br[j] == 0xFFFFFFFFu) continue;
+            const u32 o = tile_base[br[j] & 0xFFu] + (br[j] >> 8);
+            out_keys[o] = key[j];
+            out_vals[o] = val[j];
+        }
+        tile_cnt[tid] = 0;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Generic multi-block exclusive scan (u64), chunk = 4096 elements per CTA
 // ---------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 256;

@@ -175,7 +175,7 @@ def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, wo
         sh.exchange(L.VB_XCHG_P2P if (p2p and group_op) else L.VB_XCHG_NCCL)
         if stats is not None:
             for k_, v_ in sh.exchange_stats().items():
-                stats[k_] = (stats.get(k_, 0) + v_) if k_ in ("exchange_ms", "exchanges") else v_
+                stats[k_] = (stats.get(k_, 0) + v_) if k_ in ("exchange_ms", "exchanges", "prepare_wall_ms", "counts_wall_ms", "post_wall_ms") else v_
     elif world > 1 and p2p and agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP) and isinstance(engine, CudaEngine):
         p2p_exchange(engine, sh, rank, world, group, stats)
     elif world > 1:

@@ -256,7 +256,8 @@ class Shuffle:
         st = L.vb_xstats()
         L.check(self._lib.vb_shuffle_exchange_stats(self._h, ctypes.byref(st)))
         return {"sent_rows": st.sent_rows, "recv_rows": st.recv_rows, "exchanges": st.exchanges,
-                "exchange_ms": st.exchange_ms, "exchange_kind": {0: None, 1: "nccl", 2: "p2p"}[st.kind]}
+                "exchange_ms": st.exchange_ms, "exchange_kind": {0: None, 1: "nccl", 2: "p2p"}[st.kind],
+                "prepare_wall_ms": st.prepare_wall_ms, "counts_wall_ms": st.counts_wall_ms, "post_wall_ms": st.post_wall_ms}
 
     def seal(self):
         L.check(self._lib.vb_shuffle_seal(self._h))
