@@ -780,3 +780,28 @@ print("sweep ok")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0 and "sweep ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_zipf_hot_key_cache_over_many_tiles_matches_oracle(sc):
+    """Enough rows per map task (> 16 tiles per CTA) for the CTAs to finish their learning tiles and keep using
+    the hot-key cache and its flush at CTA exit over many tiles: sums, extrema, counts and f64 sums
+    must still equal the oracle's for every key."""
+    import torch
+    n, D = 24_000_000, 200_000
+    rows = torch.empty((n, 2), dtype=torch.int64, device="cuda")
+    sc.gen_pairs(out_rows=rows, first=0, n=n, mode="zipf", n_distinct=D, seed_k=7, seed_v=3, zipf_s=1.1)
+    host = rows.cpu().numpy().view(np.uint64)
+    keys, vals = host[:, 0].copy(), host[:, 1].copy()
+    for op in ("sum", "max", "min"):
+        got = gpu_reduce_parts(sc.make_rdd(rows, 2).reduce_by_key(op, 5))
+        got = [{k & (2 ** 64 - 1): v & (2 ** 64 - 1) for k, v in d.items()} for d in got]
+        assert got == oracle_reduce(op, keys, vals, 2, 5), op
+    got = gpu_reduce_parts(sc.make_rdd(rows, 2).count_by_key(5))
+    assert [{k & (2 ** 64 - 1): v for k, v in d.items()} for d in got] == oracle_reduce("count", keys, vals, 2, 5)
+    fv = vals.astype(np.float64) / 2 ** 20
+    gotf = gpu_reduce_parts(sc.make_rdd((keys, fv), 2).reduce_by_key("sum", 5))      # host SoA input: register/bulk staged path
+    wantf = oracle_reduce("sum", keys, fv, 2, 5, "f64")
+    for g, w in zip(gotf, wantf):
+        assert set(g) == set(w)
+        for k in list(w)[:: max(1, len(w) // 2000)]:
+            assert g[k] == pytest.approx(w[k], rel=1e-6)

@@ -173,9 +173,11 @@ def run_shuffle(engine, local_maps, n_map, n_reduce, kcode, vcode, agg, rank, wo
         # libvega_b200, on the library's stream; torch.distributed is not involved
         group_op = agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP)
         sh.exchange(L.VB_XCHG_P2P if (p2p and group_op) else L.VB_XCHG_NCCL)
-        if stats is not None:
+        engine.seal(sh)
+        if stats is not None:           # after the seal: reading the event timers synchronises the stream
             for k_, v_ in sh.exchange_stats().items():
                 stats[k_] = (stats.get(k_, 0) + v_) if k_ in ("exchange_ms", "exchanges", "prepare_wall_ms", "counts_wall_ms", "post_wall_ms") else v_
+        return sh
     elif world > 1 and p2p and agg in (L.VB_AGG_GROUP, L.VB_AGG_COGROUP) and isinstance(engine, CudaEngine):
         p2p_exchange(engine, sh, rank, world, group, stats)
     elif world > 1:
