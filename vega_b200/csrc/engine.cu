@@ -797,6 +797,7 @@ static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
     u64 tiles = (n + RP_TILE - 1) / RP_TILE;
     u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
     u64 tiles_per_part = (tiles + parts - 1) / parts;
+    if (bits == 8 && tiles_per_part > 3) tiles_per_part = (tiles_per_part + 2) / 3 * 3;   // 12288-row units: a multiple of every sweep tile (3072 / 4096 / 6144 rows)
     p.rows_per_part = tiles_per_part * RP_TILE;
     p.num_parts = (u32)((n + p.rows_per_part - 1) / p.rows_per_part);
     return p;
@@ -837,6 +838,9 @@ static int radix_hist_scan(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n,
 }
 
 template <typename KeyT, bool HAS_VAL>
+static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist, size_t *smem, const void **kern_static = nullptr);
+
+template <typename KeyT, bool HAS_VAL>
 static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist,
                       const PassPlan &plan)
 {
@@ -846,6 +850,28 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode, bits);
     if (!sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d / %d bits not instantiated", ld.mode, dg.mode, bits);
     TRY((radix_hist_scan<KeyT>(s, ld, dg, n, d_hist, plan)));
+    {   // row streams: the sweep tile pipeline fed by the per-part offsets (no look-back)
+        static const bool off = getenv("VEGA_B200_NO_SWEEP_STATIC") != nullptr;
+        const void *k0 = nullptr, *hk0 = nullptr, *kst = nullptr;
+        size_t sm0 = 0;
+        const u32 T = sw_tile<KeyT, HAS_VAL>();
+        if (!off && bits == 8 && n < SW_MAX_ROWS * 2 && plan.rows_per_part % T == 0 && n >= 4ull * T &&
+            sweep_lookup<KeyT, HAS_VAL>(ld.mode, dg.mode, &k0, &hk0, &sm0, &kst) &&
+            !(((uintptr_t)ld.keys & 15u) || (ld.vals && ((uintptr_t)ld.vals & 15u))) && !(HAS_VAL && ld.mode != LD_AOS64 && !ld.vals)) {
+            if (c->occ_cache.find(kst) == c->occ_cache.end()) CU(cudaFuncSetAttribute(kst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+            (void)occupancy(c, kst, SW_THREADS, sm0);
+            SweepArgs a{};
+            a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = (u32)((n + T - 1) / T);
+            a.tile_counter = nullptr; a.state = nullptr; a.digit_base = nullptr;
+            a.out_keys = out_keys; a.out_vals = out_vals;
+            a.part_off = d_hist; a.num_parts = plan.num_parts; a.rows_per_part = plan.rows_per_part;
+            Digit dgs = dg;
+            KLaunch kl(s, K_RP_SCATTER, n);
+            void *args[] = {&a, &dgs};
+            CU(cudaLaunchKernel(kst, dim3(plan.num_parts), dim3(SW_THREADS), args, sm0, c->stream));
+            return kl.done("rp_sweep_kernel<STATIC>");
+        }
+    }
     const size_t smem = scatter_smem<KeyT, HAS_VAL>(bits);
     CU(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     u64 rows_per_part = plan.rows_per_part;
@@ -871,11 +897,12 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
 #define SW_COMBOS_U32V(X) X(LD_KEY32_VAL_SOA, DG_BITS) X(LD_KEY32_VAL_AOS, DG_BITS)
 
 template <typename KeyT, bool HAS_VAL>
-static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist, size_t *smem)
+static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist, size_t *smem, const void **kern_static)
 {
 #define X(L, D)                                                                                   \
     if (ldm == L && dgm == D) {                                                                   \
         *kern = (const void *)rp_sweep_kernel<KeyT, HAS_VAL, L, D>;                               \
+        if (kern_static) *kern_static = (const void *)rp_sweep_kernel<KeyT, HAS_VAL, L, D, true>; \
         *hist = (const void *)sw_hist_all_kernel<KeyT, L, D>;                                     \
         *smem = SwSmem<KeyT, HAS_VAL, L>::total;                                                  \
         return true;                                                                              \

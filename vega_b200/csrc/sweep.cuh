@@ -56,6 +56,11 @@ struct SweepArgs {
     const u32 *digit_base;    // [256] exclusive scan of the global histogram of this pass's digit
     void *out_keys;
     u64 *out_vals;
+    // STATIC variant (no look-back): CTA p owns the contiguous rows [p*rows_per_part, (p+1)*rows_per_part) and starts
+    // digit d at part_off[d*num_parts + p] (the scanned per-part histogram of rp_hist_kernel + rp_scan_kernel)
+    const u32 *part_off;
+    u32 num_parts;
+    u64 rows_per_part;        // multiple of the tile size
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -134,7 +139,12 @@ VB_D u32 ld_relaxed_u32(const u32 *p)
 }
 VB_D void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-template <typename KeyT, bool HAS_VAL, int LDM, int DGM>
+// STATIC = false: tiles claimed from an atomic counter, digit offsets by decoupled look-back (one kernel per pass).
+// STATIC = true : the same tile pipeline (copy-engine staging, warp-private u16 counters, 4 barriers, full-tile fast path)
+//                 fed by the per-part histogram of rp_hist/rp_scan: each CTA walks its own contiguous part and keeps
+//                 running digit offsets in shared memory — no status words, no polling.  This is the product's scatter
+//                 for row streams (15 % faster than rp_scatter_kernel, profiles/r2_sweep_bisection.jsonl "_nolb").
+template <typename KeyT, bool HAS_VAL, int LDM, int DGM, bool STATIC = false>
 __global__ void __launch_bounds__(SW_THREADS, 2)
 rp_sweep_kernel(SweepArgs a, Digit dg)
 {
@@ -159,6 +169,7 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
     __shared__ u32 wtot[SW_WARPS];
     __shared__ u32 dbase[SW_NB];              // tile-local start of digit d
     __shared__ u32 gbase[SW_NB];              // global offset of digit d's first row of this tile, minus dbase[d]
+    __shared__ u32 run_off[STATIC ? SW_NB : 1];   // STATIC: global offset of the next row of digit d of this part
 
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const u32 lt = lanemask_lt();
@@ -177,10 +188,15 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
     };
     auto tile_is_full = [&](u32 t) { return (u64)(t + 1) * T <= n; };
 
+    // STATIC: this CTA's tiles are [part_first, part_last); a.n_tiles doubles as the "no more tiles" sentinel
+    const u32 part_first = STATIC ? (u32)(((u64)blockIdx.x * a.rows_per_part) / T) : 0u;
+    const u32 part_last = STATIC ? (u32)min((u64)a.n_tiles, (((u64)blockIdx.x + 1) * a.rows_per_part) / T) : 0u;
+    if (STATIC)
+        for (u32 d = tid; d < SW_NB; d += SW_THREADS) run_off[d] = a.part_off[(size_t)d * a.num_parts + blockIdx.x];
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         mbar_fence_init();
-        const u32 t0 = atomicAdd(a.tile_counter, 1u);
+        const u32 t0 = STATIC ? (part_first < part_last ? part_first : a.n_tiles) : atomicAdd(a.tile_counter, 1u);
         s_tile[0] = t0;
         if (t0 < a.n_tiles && tile_is_full(t0)) issue_tile(t0);
     }
@@ -259,7 +275,7 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
         }
         __syncthreads();                                                        // B1: counters complete, raw buffer consumed
         if (tid == 0) {                                                          // claim + prefetch the next tile
-            const u32 nx = atomicAdd(a.tile_counter, 1u);
+            const u32 nx = STATIC ? (tile + 1 < part_last ? tile + 1 : a.n_tiles) : atomicAdd(a.tile_counter, 1u);
             s_tile[(it + 1) & 1u] = nx;
             if (nx < a.n_tiles && tile_is_full(nx)) issue_tile(nx);
         }
@@ -269,8 +285,10 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
         if (tid < SW_NB) {
 #pragma unroll
             for (int w = 0; w < SW_WARPS; ++w) { const u32 c = cnt[w * SW_NB + tid]; cnt[w * SW_NB + tid] = (unsigned short)total; total += c; }
-            if (tile == 0) st_relaxed_u32(&a.state[tid], SW_FLAG_INC | total);
-            else st_relaxed_u32(&a.state[(size_t)tile * SW_NB + tid], SW_FLAG_AGG | total);
+            if (!STATIC) {
+                if (tile == 0) st_relaxed_u32(&a.state[tid], SW_FLAG_INC | total);
+                else st_relaxed_u32(&a.state[(size_t)tile * SW_NB + tid], SW_FLAG_AGG | total);
+            }
         }
         u32 incl = total;
 #pragma unroll
@@ -301,7 +319,9 @@ rp_sweep_kernel(SweepArgs a, Digit dg)
         // dead (room for a window of SW_LB status words in flight per thread) and the predecessors have had the whole
         // staging phase to publish.  A serial one-tile-per-L2-round-trip walk cannot keep up with > 10 tiles/us
         // chip-wide (measured: 3x slower than the two-kernel pass), so SW_LB predecessors are fetched per step.
-        if (tid < SW_NB) {
+        if (STATIC) {
+            if (tid < SW_NB) { const u32 ro = run_off[tid]; gbase[tid] = ro - excl_local; run_off[tid] = ro + total; }
+        } else if (tid < SW_NB) {
             u32 prefix = 0;
 #ifdef VB_SW_DEBUG_NOLB          // timing bisection only: results are wrong
             if (false) {
