@@ -914,11 +914,11 @@ static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist,
     return false;
 }
 
-// The one-kernel pass is OPT-IN (VEGA_B200_SWEEP=1).  Measured on B200 (profiles/r2_sweep_bisection.jsonl,
-// profiles/r2_ncu_sweep.txt): without its look-back it is 15 % faster than rp_scatter_kernel (7.6 vs 8.9 ms per
-// 1e9-row pass of (u32,u64) rows), but at ~22 tiles/us chip-wide the decoupled look-back needs ~40 predecessors per
-// tile (three windows of 16 status words, each an L2 round trip spent behind a barrier) and costs 3.3 ms per pass,
-// which lands the pass at 10.9 ms — on par with histogram + scan + scatter (10.2 ms), not ahead of it.
+// The one-kernel (look-back) pass is OPT-IN (VEGA_B200_SWEEP=1).  Measured on B200 (profiles/r2_sweep_bisection.jsonl,
+// profiles/r2_ncu_sweep.txt): at ~22 tiles/us chip-wide the decoupled look-back needs ~40 predecessors per tile (three
+// windows of 16 status words, each an L2 round trip spent behind a barrier) and costs ~3 ms per 1e9-row pass, which lands
+// the pass at 10.9 ms — on par with histogram + scan + scatter (10.2 ms), not ahead of it.  The same tile pipeline WITHOUT
+// the look-back (rp_sweep_kernel<STATIC>, fed by the per-part offsets) is the default scatter for row streams (radix_pass).
 static bool sweep_enabled()
 {
     static const bool on = getenv("VEGA_B200_SWEEP") != nullptr && getenv("VEGA_B200_NO_SWEEP") == nullptr;
