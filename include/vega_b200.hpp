@@ -5,6 +5,7 @@
 //   Context::new / make_rdd / parallelize          src/context.rs:333-345,399-431
 //   PairRdd::group_by_key / reduce_by_key / join   src/rdd/pair_rdd.rs:35-52,54-80,104-121
 //   Rdd::count_by_value / distinct / collect       src/rdd/rdd.rs:450-459,502-522,420-434
+//   Rdd::intersection / subtract                   src/rdd/rdd.rs:838-946
 // Rows are Vec<(K,V)> with K in {u64,i64,i32,u32} and V in {u64,i64,f64}; reduce_by_key takes a
 // named Op (the reference's serde_closure cannot cross into CUDA).  Errors throw vega::Error
 // (the reference returns Result<_> / panics).
@@ -201,6 +202,12 @@ public:
         }
         return out;
     }
+    // intersection(other[, num_splits]).collect() / subtract(other).collect()   (src/rdd/rdd.rs:838-946): the reference
+    // cogroups (x, None) of both sides and reads the two Vec lengths; here ONE tagged SUM shuffle — side A rows carry 1,
+    // side B rows 2^32 — so a key's sum says on which sides it occurred.  Each key once, like the reference.
+    std::vector<K> intersection(const KeyRddT<K> &other, size_t num_splits = 0) const { return set_op(other, num_splits, true); }
+    std::vector<K> subtract(const KeyRddT<K> &other, size_t num_splits = 0) const { return set_op(other, num_splits, false); }
+
     // distinct().collect()   (src/rdd/rdd.rs:502-522)
     std::vector<K> distinct() const
     {
@@ -210,6 +217,36 @@ public:
     }
 
 private:
+    std::vector<K> set_op(const KeyRddT<K> &other, size_t num_splits, bool both) const
+    {
+        std::vector<uint64_t> sa(std::min<uint64_t>(keys_.size(), num_slices_) + 2), sb(std::min<uint64_t>(other.keys_.size(), other.num_slices_) + 2);
+        const uint64_t na = vb_slice(keys_.size(), num_slices_, sa.data()), nb = vb_slice(other.keys_.size(), other.num_slices_, sb.data());
+        if (num_splits == 0) num_splits = (size_t)na;                       // self.number_of_splits()
+        vb_shuf *raw = nullptr;
+        check(vb_shuffle_create(sc_->raw(), sc_->new_shuffle_id(), (uint32_t)(na + nb), (uint32_t)num_splits, detail::dtype<K>::code, VB_U64,
+                                VB_AGG_SUM, VB_PART_HASH_METRO64, &raw));
+        detail::ShufPtr s(raw);
+        if (detail::dtype<K>::width == 4) check(vb_shuffle_set_key_width(raw, 4));
+        const std::vector<uint64_t> ta(keys_.size(), 1ull), tb(other.keys_.size(), 1ull << 32);
+        for (uint64_t m = 0; m < na; ++m)
+            check(vb_shuffle_map_soa(raw, (uint32_t)m, keys_.data() + sa[m], ta.data() + sa[m], sa[m + 1] - sa[m], VB_HOST));
+        for (uint64_t m = 0; m < nb; ++m)
+            check(vb_shuffle_map_soa(raw, (uint32_t)(na + m), other.keys_.data() + sb[m], tb.data() + sb[m], sb[m + 1] - sb[m], VB_HOST));
+        check(vb_shuffle_seal(raw));
+        std::vector<K> out;
+        for (uint32_t r = 0; r < num_splits; ++r) {
+            uint64_t nk = 0, nv = 0;
+            check(vb_shuffle_reduce_size(raw, r, &nk, &nv));
+            std::vector<uint64_t> k(nk), c(nk);
+            check(vb_shuffle_reduce(raw, r, k.data(), c.data(), nullptr, nullptr, VB_HOST));
+            for (uint64_t i = 0; i < nk; ++i) {
+                const bool in_a = (c[i] & 0xFFFFFFFFull) != 0, in_b = (c[i] >> 32) != 0;
+                if (both ? (in_a && in_b) : (in_a && !in_b)) out.push_back(detail::from_bits<K>(k[i]));
+            }
+        }
+        return out;
+    }
+
     std::shared_ptr<Context> sc_;
     size_t num_slices_;
     std::vector<uint64_t> keys_;

@@ -428,11 +428,12 @@ def test_config2_full_size_properties(sc):
 
 def test_cpp_host_mirror_examples_run():
     """examples/group_by.cpp and examples/join.cpp are the reference's examples/group_by.rs and
-    examples/join.rs over include/vega_b200.hpp (same data); they exit 0 only on the expected result."""
+    examples/join.rs over include/vega_b200.hpp (same data); set_ops.cpp is tests/test_rdd.rs:484-521,675-699
+    (intersection / subtract); they exit 0 only on the expected result."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for exe, needle in (("group_by", "[1, 2, 3, 4, 5, 6, 7, 8]"), ("join", "(3, (C2, (E,F)))")):
+    for exe, needle in (("group_by", "[1, 2, 3, 4, 5, 6, 7, 8]"), ("join", "(3, (C2, (E,F)))"), ("set_ops", "subtract: 0 1 2 10 12 19")):
         path = os.path.join(root, "examples", "_build", exe)
         if not os.path.exists(path):
             pytest.skip("examples not built (run __graft_entry__.build())")

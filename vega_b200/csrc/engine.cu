@@ -794,6 +794,7 @@ static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         occ = occupancy(c, kern, RPS_THREADS, smem);
     }
+    if (bits == 8) occ = std::max(occ, sw_ctas<KeyT, HAS_VAL>());   // the sweep scatter may keep more CTAs resident than rp_scatter_kernel
     u64 tiles = (n + RP_TILE - 1) / RP_TILE;
     u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
     u64 tiles_per_part = (tiles + parts - 1) / parts;
@@ -859,7 +860,7 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
             sweep_lookup<KeyT, HAS_VAL>(ld.mode, dg.mode, &k0, &hk0, &sm0, &kst) &&
             !(((uintptr_t)ld.keys & 15u) || (ld.vals && ((uintptr_t)ld.vals & 15u))) && !(HAS_VAL && ld.mode != LD_AOS64 && !ld.vals)) {
             if (c->occ_cache.find(kst) == c->occ_cache.end()) CU(cudaFuncSetAttribute(kst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
-            (void)occupancy(c, kst, SW_THREADS, sm0);
+            (void)occupancy(c, kst, sw_threads<KeyT, HAS_VAL>(), sm0);
             SweepArgs a{};
             a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = (u32)((n + T - 1) / T);
             a.tile_counter = nullptr; a.state = nullptr; a.digit_base = nullptr;
@@ -868,7 +869,7 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
             Digit dgs = dg;
             KLaunch kl(s, K_RP_SCATTER, n);
             void *args[] = {&a, &dgs};
-            CU(cudaLaunchKernel(kst, dim3(plan.num_parts), dim3(SW_THREADS), args, sm0, c->stream));
+            CU(cudaLaunchKernel(kst, dim3(plan.num_parts), dim3(sw_threads<KeyT, HAS_VAL>()), args, sm0, c->stream));
             return kl.done("rp_sweep_kernel<STATIC>");
         }
     }
@@ -979,7 +980,7 @@ static int sweep_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     const u32 tiles = (u32)((n + T - 1) / T);
     CU(cudaMemsetAsync(scratch, 0, sweep_scratch_bytes<KeyT, HAS_VAL>(n), c->stream));
     if (c->occ_cache.find(kern) == c->occ_cache.end()) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int occ = occupancy(c, kern, SW_THREADS, smem);
+    const int occ = occupancy(c, kern, sw_threads<KeyT, HAS_VAL>(), smem);
     SweepArgs a;
     a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = tiles;
     a.tile_counter = scratch; a.state = scratch + 4;
@@ -988,7 +989,7 @@ static int sweep_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     KLaunch kl(s, K_RP_SCATTER, n);
     const unsigned grid = (unsigned)std::min<u64>(tiles, (u64)c->sm_count * occ);
     void *args[] = {&a, &dgc};
-    CU(cudaLaunchKernel(kern, dim3(grid), dim3(SW_THREADS), args, smem, c->stream));
+    CU(cudaLaunchKernel(kern, dim3(grid), dim3(sw_threads<KeyT, HAS_VAL>()), args, smem, c->stream));
     return kl.done("rp_sweep_kernel");
 }
 

@@ -17,8 +17,11 @@
 
 namespace vb {
 
-constexpr int SW_THREADS = 512;
-constexpr int SW_WARPS = SW_THREADS / 32;
+// CTA shape by row type (measured on 1e9 rows, profiles/r2_sweep_cta_shape.jsonl): key-only rows run 15 % faster as 256 threads x 4 CTAs
+// per SM (3072-key tiles), rows with a value 25-30 % faster as 512 threads x 2 CTAs (4096 / 3072-row tiles: longer runs per digit).
+template <typename KeyT, bool HAS_VAL> constexpr int sw_threads() { return HAS_VAL ? 512 : 256; }
+template <typename KeyT, bool HAS_VAL> constexpr int sw_ctas() { return 1024 / sw_threads<KeyT, HAS_VAL>(); }
+constexpr int SW_MAX_CTAS = 4;
 constexpr int SW_NB = 256;
 constexpr u32 SW_FLAG_AGG = 1u << 30, SW_FLAG_INC = 2u << 30, SW_VAL_MASK = (1u << 30) - 1;   // look-back words
 #ifndef VB_SW_LB
@@ -29,7 +32,7 @@ constexpr u64 SW_MAX_ROWS = 1ull << 30;     // prefixes live in 30 bits; larger 
 
 // items per thread by row width: both tile buffers (raw + staged) of 2 resident CTAs fit the 227 KB of an SM
 template <typename KeyT, bool HAS_VAL> constexpr int sw_items() { return (sizeof(KeyT) + (HAS_VAL ? 8 : 0)) >= 16 ? 6 : (sizeof(KeyT) + (HAS_VAL ? 8 : 0)) == 12 ? 8 : 12; }
-template <typename KeyT, bool HAS_VAL> constexpr int sw_tile() { return SW_THREADS * sw_items<KeyT, HAS_VAL>(); }
+template <typename KeyT, bool HAS_VAL> constexpr int sw_tile() { return sw_threads<KeyT, HAS_VAL>() * sw_items<KeyT, HAS_VAL>(); }
 
 // shared-memory plan (bytes): [raw vals | raw keys] [staged vals | staged keys | staged digit] [warp counters u16]
 template <typename KeyT, bool HAS_VAL, int LDM>
@@ -42,7 +45,7 @@ struct SwSmem {
     static constexpr size_t st_vals = HAS_VAL ? (size_t)T * 8 : 0;
     static constexpr size_t st_keys = (size_t)T * sizeof(KeyT);
     static constexpr size_t st_dig = (size_t)T;
-    static constexpr size_t cnt = (size_t)SW_WARPS * SW_NB * 2;
+    static constexpr size_t cnt = (size_t)(sw_threads<KeyT, HAS_VAL>() / 32) * SW_NB * 2;
     static constexpr size_t total = raw + st_vals + st_keys + st_dig + cnt;
 };
 
@@ -146,9 +149,12 @@ VB_D void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u3
 //                 for row streams: 2 % (12-byte rows, 8-byte keys) to 8 % ((u64,u64) rows, which rp_scatter_kernel cannot
 //                 prefetch) faster than rp_scatter_kernel on 1e9 rows (profiles/r2_ops_1e9.jsonl vs r2_ops_1e9_rp_scatter.jsonl).
 template <typename KeyT, bool HAS_VAL, int LDM, int DGM, bool STATIC = false>
-__global__ void __launch_bounds__(SW_THREADS, 2)
+__global__ void __launch_bounds__((sw_threads<KeyT, HAS_VAL>()), (sw_ctas<KeyT, HAS_VAL>()))
 rp_sweep_kernel(SweepArgs a, Digit dg)
 {
+    constexpr int SW_THREADS = sw_threads<KeyT, HAS_VAL>();
+    constexpr int SW_WARPS = SW_THREADS / 32;
+    static_assert(SW_NB <= SW_THREADS, "one thread per digit in the column scan");
     using SM = SwSmem<KeyT, HAS_VAL, LDM>;
     constexpr int K = sw_items<KeyT, HAS_VAL>();
     constexpr int T = SM::T;
