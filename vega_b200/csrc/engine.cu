@@ -798,7 +798,7 @@ static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
     u64 tiles = (n + RP_TILE - 1) / RP_TILE;
     u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
     u64 tiles_per_part = (tiles + parts - 1) / parts;
-    if (bits == 8 && tiles_per_part > 3) tiles_per_part = (tiles_per_part + 2) / 3 * 3;   // 12288-row units: a multiple of every sweep tile (3072 / 4096 / 6144 rows)
+    if (bits == 8 && tiles_per_part > 6) tiles_per_part = (tiles_per_part + 5) / 6 * 6;   // 24576-row units: a multiple of every sweep tile (3072 ... 8192 rows)
     p.rows_per_part = tiles_per_part * RP_TILE;
     p.num_parts = (u32)((n + p.rows_per_part - 1) / p.rows_per_part);
     return p;

@@ -17,9 +17,19 @@
 
 namespace vb {
 
-// CTA shape by row type (measured on 1e9 rows, profiles/r2_sweep_cta_shape.jsonl): key-only rows run 15 % faster as 256 threads x 4 CTAs
-// per SM (3072-key tiles), rows with a value 25-30 % faster as 512 threads x 2 CTAs (4096 / 3072-row tiles: longer runs per digit).
-template <typename KeyT, bool HAS_VAL> constexpr int sw_threads() { return HAS_VAL ? 512 : 256; }
+// CTA shape by row type (measured on 1e9 rows, profiles/r2_sweep_cta_shape.jsonl): key-only rows run fastest as 256 threads x 4 CTAs
+// per SM (3072-key tiles: 50.9 ms for 8 passes vs 59.7 as 512 x 2 and 61.9 as 256 x 16 keys); rows with a value want the longest runs
+// per digit: 1024 threads x 1 CTA (8192-row tiles of (u32,u64), 6144 of (u64,u64)) beats 512 x 2 by 4-8 % and 256 x 4 by 30 %.
+#ifndef VB_SW_THREADS_VAL
+#define VB_SW_THREADS_VAL 1024
+#endif
+#ifndef VB_SW_THREADS_KEY
+#define VB_SW_THREADS_KEY 256
+#endif
+#ifndef VB_SW_ITEMS_KEY
+#define VB_SW_ITEMS_KEY 12
+#endif
+template <typename KeyT, bool HAS_VAL> constexpr int sw_threads() { return HAS_VAL ? VB_SW_THREADS_VAL : VB_SW_THREADS_KEY; }
 template <typename KeyT, bool HAS_VAL> constexpr int sw_ctas() { return 1024 / sw_threads<KeyT, HAS_VAL>(); }
 constexpr int SW_MAX_CTAS = 4;
 constexpr int SW_NB = 256;
@@ -30,8 +40,8 @@ constexpr u32 SW_FLAG_AGG = 1u << 30, SW_FLAG_INC = 2u << 30, SW_VAL_MASK = (1u 
 constexpr int SW_LB = VB_SW_LB;            // look-back window: status words fetched per step
 constexpr u64 SW_MAX_ROWS = 1ull << 30;     // prefixes live in 30 bits; larger inputs use the rp_* kernels
 
-// items per thread by row width: both tile buffers (raw + staged) of 2 resident CTAs fit the 227 KB of an SM
-template <typename KeyT, bool HAS_VAL> constexpr int sw_items() { return (sizeof(KeyT) + (HAS_VAL ? 8 : 0)) >= 16 ? 6 : (sizeof(KeyT) + (HAS_VAL ? 8 : 0)) == 12 ? 8 : 12; }
+// items per thread by row width: the tile buffers (raw + staged) of the resident CTAs fit the 227 KB of an SM
+template <typename KeyT, bool HAS_VAL> constexpr int sw_items() { return (sizeof(KeyT) + (HAS_VAL ? 8 : 0)) >= 16 ? 6 : (sizeof(KeyT) + (HAS_VAL ? 8 : 0)) == 12 ? 8 : VB_SW_ITEMS_KEY; }
 template <typename KeyT, bool HAS_VAL> constexpr int sw_tile() { return sw_threads<KeyT, HAS_VAL>() * sw_items<KeyT, HAS_VAL>(); }
 
 // shared-memory plan (bytes): [raw vals | raw keys] [staged vals | staged keys | staged digit] [warp counters u16]
