@@ -156,8 +156,8 @@ VB_D void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u3
 // STATIC = true : the same tile pipeline (copy-engine staging, warp-private u16 counters, 4 barriers, full-tile fast path)
 //                 fed by the per-part histogram of rp_hist/rp_scan: each CTA walks its own contiguous part and keeps
 //                 running digit offsets in shared memory — no status words, no polling.  This is the product's scatter
-//                 for row streams: 2 % (12-byte rows, 8-byte keys) to 8 % ((u64,u64) rows, which rp_scatter_kernel cannot
-//                 prefetch) faster than rp_scatter_kernel on 1e9 rows (profiles/r2_ops_1e9.jsonl vs r2_ops_1e9_rp_scatter.jsonl).
+//                 for row streams: with the CTA shape picked per row type (sw_threads) 8-15 % faster than rp_scatter_kernel
+//                 on 1e9 rows (profiles/r2_ops_1e9.jsonl vs r2_ops_1e9_rp_scatter.jsonl, r2_sweep_cta_shape.jsonl).
 template <typename KeyT, bool HAS_VAL, int LDM, int DGM, bool STATIC = false>
 __global__ void __launch_bounds__((sw_threads<KeyT, HAS_VAL>()), (sw_ctas<KeyT, HAS_VAL>()))
 rp_sweep_kernel(SweepArgs a, Digit dg)
