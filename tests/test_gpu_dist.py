@@ -190,6 +190,8 @@ def test_two_rank_join_and_cogroup_match_oracle(Ma, Mb, R, p2p):
 # ---------------------------------------------------------------------------------------------
 def _sort_dataset(kdtype):
     rng = np.random.default_rng(5)
+    if kdtype == "tiny":          # 3 rows, more partitions than rows: one rank holds a single row, most partitions are empty
+        return np.array([7, 7, 2], dtype=np.uint64), np.arange(3, dtype=np.uint64)
     n = 150_000
     if kdtype == "u64":
         keys = rng.integers(0, 3000, n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)     # many duplicates
@@ -217,7 +219,7 @@ def _sort_worker(rank, world, port, kdtype, M, R, payload, outdir):
     starts = vb.slice_starts(len(keys), M)
     lo, hi = vdist.map_block(rank, world, M)
     maps = [(m, keys[starts[m]:starts[m + 1]], vals[starts[m]:starts[m + 1]] if payload else None) for m in range(lo, hi)]
-    kcode = {"u64": L.VB_U64, "i64": L.VB_I64, "f64": L.VB_F64}[kdtype]
+    kcode = {"u64": L.VB_U64, "i64": L.VB_I64, "f64": L.VB_F64, "tiny": L.VB_U64}[kdtype]
     sh = vdist.run_shuffle(eng, maps, M, R, kcode, L.VB_U64, L.VB_AGG_SORT, rank, world)
     sh.has_payload = payload
     res = {r: [None if x is None else np.asarray(x) for x in sh.reduce(r)] for r in range(R)}
@@ -228,7 +230,8 @@ def _sort_worker(rank, world, port, kdtype, M, R, payload, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kdtype,M,R,payload", [("u64", 4, 4, True), ("i64", 5, 6, True), ("f64", 2, 3, False), ("u64", 3, 2, False)])
+@pytest.mark.parametrize("kdtype,M,R,payload", [("u64", 4, 4, True), ("i64", 5, 6, True), ("f64", 2, 3, False), ("u64", 3, 2, False),
+                                               ("tiny", 2, 5, True)])
 def test_two_rank_sort_by_key_matches_oracle(kdtype, M, R, payload):
     if torch.cuda.device_count() < 2:
         pytest.skip("multi-rank sort_by_key runs through the library's NCCL communicator: needs >= 2 GPUs")
@@ -238,7 +241,7 @@ def test_two_rank_sort_by_key_matches_oracle(kdtype, M, R, payload):
         mp.spawn(_sort_worker, args=(world, _free_port(), kdtype, M, R, payload, d), nprocs=world, join=True)
         per_rank = [pickle.load(open(os.path.join(d, f"s{r}.pkl"), "rb")) for r in range(world)]
     keys, vals = _sort_dataset(kdtype)
-    ok, ov, ps = O.sort_by_key(keys, vals if payload else None, R, kdtype)
+    ok, ov, ps = O.sort_by_key(keys, vals if payload else None, R, "u64" if kdtype == "tiny" else kdtype)
     for r in range(R):
         gk, gv = per_rank[r % world][r]
         a, b = int(ps[r]), int(ps[r + 1])
