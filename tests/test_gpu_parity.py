@@ -806,3 +806,58 @@ def test_zipf_hot_key_cache_over_many_tiles_matches_oracle(sc):
         assert set(g) == set(w)
         for k in list(w)[:: max(1, len(w) // 2000)]:
             assert g[k] == pytest.approx(w[k], rel=1e-6)
+
+
+def _medium_sort_and_group_cases(sc):
+    """Sizes at which every part of a radix pass holds several FULL tiles of the gather sweep plus a partial one
+    (the small cases above only ever see partial tiles): key-only and (key, value) sorts with every order transform,
+    group_by_key from SoA columns and from device AoS rows (ids + values inside 16-byte rows in the first pass)."""
+    import torch
+    rng = np.random.default_rng(77)
+    for kd, n in (("u64", 5_000_003), ("i64", 3_000_001), ("f64", 2_500_000)):
+        if kd == "u64":
+            k = rng.integers(0, 1 << 63, n).astype(np.uint64) * np.uint64(2) + rng.integers(0, 2, n).astype(np.uint64)
+        elif kd == "i64":
+            k = rng.integers(-(1 << 62), 1 << 62, n).astype(np.int64)
+        else:
+            k = rng.standard_normal(n) * 1e9
+        k[::5] = k[11]                      # a long run of equal keys: stability across tiles and parts
+        v = np.arange(n, dtype=np.uint64)
+        ok, ov, ps = O.sort_by_key(k, v, 8, kd)
+        gk, gv = sc.parallelize((k, v), 5).sort_by_key(8).collect()
+        assert np.array_equal(gk.view(np.uint64), ok.view(np.uint64)) and np.array_equal(gv.view(np.uint64), ov), kd
+        gk2, _ = sc.parallelize(k, 3).sort(8).collect()
+        assert np.array_equal(gk2.view(np.uint64), ok.view(np.uint64)), kd
+    keys, vals = rand_pairs(rng, 4_000_000, 300_000)
+    want = oracle_group(keys, vals, 6, 8)
+    assert gpu_group_parts(sc.parallelize((keys, vals), 6).group_by_key(8)) == want
+    rows = torch.from_numpy(np.stack([keys, vals], axis=1).view(np.int64)).cuda()
+    got = gpu_group_parts(sc.parallelize(rows, 6).group_by_key(8))         # int64 rows: keys come back signed
+    assert [{k & (2 ** 64 - 1): v for k, v in d.items()} for d in got] == want
+    keys, vals = rand_pairs(rng, 3_000_000, 37)           # 37 keys: one pass, runs of ~80k rows per digit
+    assert gpu_group_parts(sc.parallelize((keys, vals), 4).group_by_key(3)) == oracle_group(keys, vals, 4, 3)
+
+
+def test_gather_sweep_full_and_partial_tiles_match_oracle(sc):
+    st = sc.parallelize(np.arange(3_000_000, dtype=np.uint64)[::-1].copy(), 2).sort(2).stats()
+    assert st["kernels"]["rp_scatter"]["launches"] >= 1
+    _medium_sort_and_group_cases(sc)
+
+
+def test_sweep_static_fallback_matches_oracle():
+    """VEGA_B200_NO_GSWEEP=1 (read once per process) sends the LSD passes back through rp_sweep_kernel<STATIC>:
+    the same medium-size cases must still match the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, vega_b200 as vb
+from tests.test_gpu_parity import _medium_sort_and_group_cases
+with vb.Context(0) as sc:
+    _medium_sort_and_group_cases(sc)
+print("fallback ok")
+'''
+    env = dict(os.environ, VEGA_B200_NO_GSWEEP="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "fallback ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -17,6 +17,8 @@
 #include "../../include/vega_b200.h"
 #include "kernels.cuh"
 #include "sweep.cuh"
+#include "gsweep.cuh"
+#include <type_traits>
 
 using namespace vb;
 
@@ -778,6 +780,30 @@ static size_t scatter_smem(int bits)
     return bits == 8 ? rp_scatter_smem<KeyT, HAS_VAL, 8>() : rp_scatter_smem<KeyT, HAS_VAL, RP_SORT_BITS>();
 }
 
+// The gather sweep (gsweep.cuh) is the scatter of the DG_BITS passes; VEGA_B200_NO_GSWEEP=1 falls back to rp_sweep_kernel<STATIC>.
+static bool gsweep_enabled()
+{
+    static const bool on = getenv("VEGA_B200_NO_GSWEEP") == nullptr;
+    return on;
+}
+
+template <typename KeyT, bool HAS_VAL>
+static bool gsweep_lookup(int ldm, const void **kern, size_t *smem, u32 *tile)
+{
+#define X(L)                                                                 \
+    if (ldm == L) {                                                          \
+        if constexpr (rp_key_ok<KeyT, L>() && (HAS_VAL || L == LD_SOA64)) { \
+            *kern = (const void *)rp_gsweep_kernel<KeyT, HAS_VAL, L>;        \
+            *smem = GsPlan<KeyT, HAS_VAL, L>::total;                         \
+            *tile = (u32)GsPlan<KeyT, HAS_VAL, L>::T;                        \
+            return true;                                                     \
+        }                                                                    \
+    }
+    X(LD_SOA64) X(LD_AOS64) X(LD_KEY32_VAL_SOA) X(LD_KEY32_VAL_AOS)
+#undef X
+    return false;
+}
+
 template <typename KeyT, bool HAS_VAL>
 static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
 {
@@ -794,7 +820,7 @@ static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         occ = occupancy(c, kern, RPS_THREADS, smem);
     }
-    if (bits == 8) occ = std::max(occ, sw_ctas<KeyT, HAS_VAL>());   // the sweep scatter may keep more CTAs resident than rp_scatter_kernel
+    if (bits == 8) occ = gsweep_enabled() ? 1024 / VB_GS_THREADS : std::max(occ, sw_ctas<KeyT, HAS_VAL>());   // one part per resident CTA of the scatter that will run
     u64 tiles = (n + RP_TILE - 1) / RP_TILE;
     u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
     u64 tiles_per_part = (tiles + parts - 1) / parts;
@@ -851,6 +877,28 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     const void *sk = scatter_fn<KeyT, HAS_VAL>(ld.mode, dg.mode, bits);
     if (!sk) return set_err(VB_ERR_UNSUPPORTED, "radix pass: loader %d / digit %d / %d bits not instantiated", ld.mode, dg.mode, bits);
     TRY((radix_hist_scan<KeyT>(s, ld, dg, n, d_hist, plan)));
+    {   // LSD digit passes over row streams: the gather sweep (two 512-thread CTAs per SM, rows stay where the copy engine put them)
+        const void *gk = nullptr;
+        size_t gsm = 0;
+        u32 GT = 0;
+        if (gsweep_enabled() && bits == 8 && dg.mode == DG_BITS && n < SW_MAX_ROWS * 2 && plan.rows_per_part % 4096 == 0 &&
+            gsweep_lookup<KeyT, HAS_VAL>(ld.mode, &gk, &gsm, &GT) && n >= 4ull * GT &&
+            !(((uintptr_t)ld.keys & 15u) || (ld.vals && ((uintptr_t)ld.vals & 15u))) && !(HAS_VAL && ld.mode != LD_AOS64 && !ld.vals)) {
+            if (c->occ_cache.find(gk) == c->occ_cache.end()) CU(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+            (void)occupancy(c, gk, VB_GS_THREADS, gsm);
+            SweepArgs a{};
+            a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = 0;
+            a.out_keys = out_keys; a.out_vals = out_vals;
+            a.part_off = d_hist; a.num_parts = plan.num_parts; a.rows_per_part = plan.rows_per_part;
+            static const u32 stagger = getenv("VEGA_B200_GS_STAGGER") ? (u32)atoi(getenv("VEGA_B200_GS_STAGGER")) : 0u;
+            a.stagger_ns = stagger;
+            Digit dgs = dg;
+            KLaunch kl(s, K_RP_SCATTER, n);
+            void *args[] = {&a, &dgs};
+            CU(cudaLaunchKernel(gk, dim3(plan.num_parts), dim3(VB_GS_THREADS), args, gsm, c->stream));
+            return kl.done("rp_gsweep_kernel");
+        }
+    }
     {   // row streams: the sweep tile pipeline fed by the per-part offsets (no look-back)
         static const bool off = getenv("VEGA_B200_NO_SWEEP_STATIC") != nullptr;
         const void *k0 = nullptr, *hk0 = nullptr, *kst = nullptr;
