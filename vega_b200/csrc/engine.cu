@@ -788,7 +788,7 @@ static bool gsweep_enabled()
 }
 
 template <typename KeyT, bool HAS_VAL>
-static bool gsweep_lookup(int ldm, const void **kern, size_t *smem, u32 *tile)
+static bool gsweep_lookup(int ldm, const void **kern, size_t *smem, u32 *tile, u32 *threads)
 {
 #define X(L)                                                                 \
     if (ldm == L) {                                                          \
@@ -796,6 +796,7 @@ static bool gsweep_lookup(int ldm, const void **kern, size_t *smem, u32 *tile)
             *kern = (const void *)rp_gsweep_kernel<KeyT, HAS_VAL, L>;        \
             *smem = GsPlan<KeyT, HAS_VAL, L>::total;                         \
             *tile = (u32)GsPlan<KeyT, HAS_VAL, L>::T;                        \
+            *threads = (u32)GsPlan<KeyT, HAS_VAL, L>::THREADS;               \
             return true;                                                     \
         }                                                                    \
     }
@@ -820,7 +821,8 @@ static PassPlan plan_pass(vb_ctx *c, u64 n, int bits)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         occ = occupancy(c, kern, RPS_THREADS, smem);
     }
-    if (bits == 8) occ = gsweep_enabled() ? 1024 / VB_GS_THREADS : std::max(occ, sw_ctas<KeyT, HAS_VAL>());   // one part per resident CTA of the scatter that will run
+    if (bits == 8) occ = gsweep_enabled() ? GsPlan<KeyT, HAS_VAL, (sizeof(KeyT) == 4 ? LD_KEY32_VAL_SOA : LD_SOA64)>::CTAS
+                                          : std::max(occ, sw_ctas<KeyT, HAS_VAL>());   // one part per resident CTA of the scatter that will run
     u64 tiles = (n + RP_TILE - 1) / RP_TILE;
     u64 parts = std::min<u64>(tiles, (u64)c->sm_count * occ);
     u64 tiles_per_part = (tiles + parts - 1) / parts;
@@ -880,12 +882,12 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
     {   // LSD digit passes over row streams: the gather sweep (two 512-thread CTAs per SM, rows stay where the copy engine put them)
         const void *gk = nullptr;
         size_t gsm = 0;
-        u32 GT = 0;
+        u32 GT = 0, gthreads = 0;
         if (gsweep_enabled() && bits == 8 && dg.mode == DG_BITS && n < SW_MAX_ROWS * 2 && plan.rows_per_part % 4096 == 0 &&
-            gsweep_lookup<KeyT, HAS_VAL>(ld.mode, &gk, &gsm, &GT) && n >= 4ull * GT &&
+            gsweep_lookup<KeyT, HAS_VAL>(ld.mode, &gk, &gsm, &GT, &gthreads) && n >= 4ull * GT &&
             !(((uintptr_t)ld.keys & 15u) || (ld.vals && ((uintptr_t)ld.vals & 15u))) && !(HAS_VAL && ld.mode != LD_AOS64 && !ld.vals)) {
             if (c->occ_cache.find(gk) == c->occ_cache.end()) CU(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-            (void)occupancy(c, gk, VB_GS_THREADS, gsm);
+            (void)occupancy(c, gk, (int)gthreads, gsm);
             SweepArgs a{};
             a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = 0;
             a.out_keys = out_keys; a.out_vals = out_vals;
@@ -895,7 +897,7 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
             Digit dgs = dg;
             KLaunch kl(s, K_RP_SCATTER, n);
             void *args[] = {&a, &dgs};
-            CU(cudaLaunchKernel(gk, dim3(plan.num_parts), dim3(VB_GS_THREADS), args, gsm, c->stream));
+            CU(cudaLaunchKernel(gk, dim3(plan.num_parts), dim3(gthreads), args, gsm, c->stream));
             return kl.done("rp_gsweep_kernel");
         }
     }
@@ -1207,10 +1209,16 @@ static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, 
 // LSD radix sort of (u32 id, u64 val) pairs over `bits` low bits.  ids_a is overwritten.
 // The first pass reads values through `first` (ids come from ids_a).  Results: *out_ids, *out_vals
 // (owned by the caller afterwards).
-static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32 bits, u32 **out_ids, u64 **out_vals)
+static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32 bits, u32 **out_ids, u64 **out_vals, const u32 *xlat = nullptr)
 {
     vb_ctx *c = s->ctx;
     const u32 passes = std::max<u32>(1, (bits + RP_SORT_BITS - 1) / RP_SORT_BITS);
+    auto translate_now = [&]() -> int {       // the stand-alone translation (paths whose first histogram does not go through rp_hist_kernel)
+        KLaunch kl(s, K_MISC);
+        u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8);
+        translate_ids_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(ids_a, n, xlat);
+        return kl.done("translate_ids_kernel");
+    };
     {
         Loader probe = first;
         probe.keys = ids_a;
@@ -1218,6 +1226,7 @@ static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32
         dgp.mode = DG_BITS;
         if (sweep_applicable<u32, true>(probe, dgp, n) && RP_SORT_BITS == 8) {
             // sweep path: ONE histogram read for all digit positions, then one look-back kernel per pass
+            if (xlat) TRY(translate_now());
             DevBuf bases(c), scratch(c), ids_b(c), vals_a(c), vals_b(c);
             TRY(bases.alloc((size_t)passes * SW_NB * 4));
             TRY(scratch.alloc((sweep_scratch_bytes<u32, true>(n))));
@@ -1260,7 +1269,7 @@ static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32
     u64 *src_vals = nullptr, *dst_vals = vals_b.as<u64>();
     for (u32 p = 0; p < passes; ++p) {
         Loader ld = first;
-        if (p == 0) ld.keys = src_ids;
+        if (p == 0) { ld.keys = src_ids; ld.xlat = xlat; }
         else ld = Loader{LD_KEY32_VAL_SOA, src_ids, src_vals, 0};
         Digit dg{};
         dg.mode = DG_BITS;
@@ -1565,18 +1574,12 @@ static int seal_group(vb_shuf *s, const Gathered &g)
         TRY(kl.done("scatter_dense_kernel"));
     }
     cslot.reset();
-    // 4. ids[i] = dense_of_slot[slot_of_row[i]]
-    {
-        KLaunch kl(s, K_MISC);
-        u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8);
-        translate_ids_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(ids.as<u32>(), n, dense.as<u32>());
-        TRY(kl.done("translate_ids_kernel"));
-    }
+    // 4. ids[i] = dense_of_slot[slot_of_row[i]]: applied by the first sort pass's histogram kernel while it counts (Loader::xlat)
     // 5. stable LSD sort of (id, value) — the reduce partition is the high part of the dense id
     Loader first = g.rows ? Loader{LD_KEY32_VAL_AOS, nullptr, g.rows, 0} : Loader{LD_KEY32_VAL_SOA, nullptr, g.vals, 0};
     u32 *sorted_ids = nullptr;
     u64 *sorted_vals = nullptr;
-    TRY(sort_id_pairs(s, ids.as<u32>(), first, n, ceil_log2_u64(std::max<u64>(D, 2)), &sorted_ids, &sorted_vals));
+    TRY(sort_id_pairs(s, ids.as<u32>(), first, n, ceil_log2_u64(std::max<u64>(D, 2)), &sorted_ids, &sorted_vals, dense.as<u32>()));
     DevBuf sid_guard(c);
     if (sorted_ids != ids.as<u32>()) sid_guard.p = sorted_ids;
     // 6. CSR offsets

@@ -18,27 +18,35 @@
 //     the full-tile path carries no validity checks.
 //
 // Stable: output order inside a digit = (part, tile, warp, item, lane) = input order, exactly as rp_sweep_kernel.
-// STATIC offsets only (per-part histogram of rp_hist_kernel + rp_scan_kernel); DG_BITS digits only.
+// Offsets from the per-part histogram (rp_hist_kernel + rp_scan_kernel), one contiguous part per CTA; DG_BITS digits only.
+// (Tried and dropped: tiles in global order with a per-tile histogram and a column scan — the scatter itself was no
+//  faster, 18.8 vs 18.9 ms for group_by_key's three passes, so the write pattern of 256 x 300 separate streams is not
+//  what bounds it, and the per-tile histogram cost 3-9 ms per pass: profiles/r2_gsweep_tile_order_tried.jsonl.)
 #pragma once
 #include "sweep.cuh"
 
 namespace vb {
 
-#ifndef VB_GS_THREADS
-#define VB_GS_THREADS 512
+// CTA shape by row type (A/B on 1e9 rows, profiles/r2_gsweep_shape_ab.jsonl): key-only rows 512 threads x 2 CTAs per SM,
+// rows with a value 1024 x 1 (the longest runs per digit)
+#ifndef VB_GS_THREADS_KEY
+#define VB_GS_THREADS_KEY 512
+#endif
+#ifndef VB_GS_THREADS_VAL
+#define VB_GS_THREADS_VAL 1024
 #endif
 // which row types keep TWO key buffers (the keys of tile t+1 land while tile t is processed; the value buffer is refilled right
 // after a tile's write-out and has the whole ranking/scan/scatter of the next tile to arrive).  bit 0: u64 key only, bit 1: (u64,u64) SoA,
 // bit 2: (u32 id, u64) SoA, bit 3: u32 id + values inside AoS rows.  AoS (u64,u64) rows arrive as one 16-byte unit: single buffer.
 #ifndef VB_GS_DB
-#define VB_GS_DB 0x1
+#define VB_GS_DB 0xF
 #endif
 
 template <typename KeyT, bool HAS_VAL, int LDM>
 struct GsPlan {
     static constexpr bool AOS = (LDM == LD_AOS64);                 // (u64,u64) rows: key and value arrive together
     static constexpr bool VAL_AOS = (LDM == LD_KEY32_VAL_AOS);     // u32 ids (SoA) + values inside 16-byte rows
-    static constexpr int THREADS = VB_GS_THREADS;
+    static constexpr int THREADS = HAS_VAL ? VB_GS_THREADS_VAL : VB_GS_THREADS_KEY;
     static constexpr int CTAS = 1024 / THREADS;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int KEY_B = AOS ? 16 : (int)sizeof(KeyT);     // bytes per row in the key buffer
@@ -109,6 +117,7 @@ rp_gsweep_kernel(SweepArgs a, Digit dg)
     const u32 lt = lanemask_lt();
     unsigned short *my_cnt = cnt + warp * SW_NB;
     const u64 pol = policy_evict_first();
+    // CTA p owns the contiguous rows [p*rows_per_part, (p+1)*rows_per_part) and starts digit d at part_off[d*num_parts + p]
     const u64 begin = (u64)blockIdx.x * a.rows_per_part;
     const u64 end = min(a.n, begin + a.rows_per_part);
     if (begin >= end) return;

@@ -598,6 +598,8 @@ struct Loader {
     const void *keys;   // u64* / u32* / rows (AoS) / table keys
     const void *vals;   // u64* (table modes: the accs array) or AoS rows for LD_KEY32_VAL_AOS
     u64 cap;            // table modes: number of regular slots (row `cap` is the special slot)
+    const u32 *xlat;    // LD_KEY32_* in rp_hist_kernel only: ids[i] = xlat[ids[i]] is applied (and stored back) while counting —
+                        // group_by_key's slot -> dense-id translation rides on the first pass's histogram read (NULL: none)
 };
 
 // Loader / digit modes are compile-time (LDM, DGM): a run-time switch per item left ptxas with a
@@ -745,6 +747,17 @@ rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ 
                 const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)(h + i) * 32 + lane;
                 key[i] = 0;
                 ok[i] = (idx < end) && rp_load_key<KeyT, LDM>(ld, idx, key[i], pol);
+            }
+            if constexpr (LDM == LD_KEY32_VAL_SOA || LDM == LD_KEY32_VAL_AOS) {
+                if (ld.xlat) {      // all HB ids are loaded before the first look-up, all look-ups issued before the first store
+#pragma unroll
+                    for (int i = 0; i < HB; ++i) if (ok[i]) key[i] = (KeyT)__ldg(ld.xlat + (u32)key[i]);
+#pragma unroll
+                    for (int i = 0; i < HB; ++i) {
+                        const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)(h + i) * 32 + lane;
+                        if (ok[i]) const_cast<u32 *>((const u32 *)ld.keys)[idx] = (u32)key[i];
+                    }
+                }
             }
 #pragma unroll
             for (int i = 0; i < HB; ++i) {
@@ -1131,11 +1144,22 @@ __global__ void translate_ids_kernel(u32 *__restrict__ ids, u64 n, const u32 *__
 // CSR offsets from sorted dense ids: offsets[id] = first row of id; offsets[n_ids] = n.
 __global__ void csr_bounds_kernel(const u32 *__restrict__ ids, u64 n, u64 *__restrict__ offsets, u64 n_ids)
 {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    // four ids per thread (one 128-bit load + the id just before them): 2.5x fewer load instructions than one id per thread
+    const u64 n4 = n / 4;
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    if (i == 0) offsets[n_ids] = n;
-    for (; i < n; i += stride) {
-        u32 id = ids[i];
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) offsets[n_ids] = n;
+    for (u64 j = t; j < n4; j += stride) {
+        const uint4 v = reinterpret_cast<const uint4 *>(ids)[j];
+        const u64 i = 4 * j;
+        const u32 prev = j ? ids[i - 1] : ~v.x;          // j == 0: anything different from v.x
+        if (prev != v.x) offsets[v.x] = i;
+        if (v.x != v.y) offsets[v.y] = i + 1;
+        if (v.y != v.z) offsets[v.z] = i + 2;
+        if (v.z != v.w) offsets[v.w] = i + 3;
+    }
+    for (u64 i = 4 * n4 + t; i < n; i += stride) {       // the last n % 4 ids
+        const u32 id = ids[i];
         if (i == 0 || ids[i - 1] != id) offsets[id] = i;
     }
 }

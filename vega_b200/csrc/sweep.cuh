@@ -74,7 +74,7 @@ struct SweepArgs {
     const u32 *part_off;
     u32 num_parts;
     u64 rows_per_part;        // multiple of the tile size
-    u32 stagger_ns;           // rp_gsweep_kernel: start delay of the second half of the grid
+    u32 stagger_ns;           // rp_gsweep_kernel: start delay of the second half of the grid (timing experiments)
 };
 
 // ---------------------------------------------------------------------------------------------
