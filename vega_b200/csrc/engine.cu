@@ -620,7 +620,8 @@ static u32 choose_log_cap(u64 total, u64 hint_distinct, bool estimated, u32 max_
 struct PassPlan;
 template <typename KeyT, bool HAS_VAL> static PassPlan plan_pass(vb_ctx *c, u64 n, int bits);
 template <typename KeyT, bool HAS_VAL>
-static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist, const PassPlan &plan);
+static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist, const PassPlan &plan,
+                      u64 *csr = nullptr, bool *csr_done = nullptr);
 
 constexpr u32 PARTITION_MIN_LOG_CAP = 24;
 
@@ -871,7 +872,7 @@ static bool sweep_lookup(int ldm, int dgm, const void **kern, const void **hist,
 
 template <typename KeyT, bool HAS_VAL>
 static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT *out_keys, u64 *out_vals, u32 *d_hist,
-                      const PassPlan &plan)
+                      const PassPlan &plan, u64 *csr, bool *csr_done)
 {
     vb_ctx *c = s->ctx;
     if (n == 0 || plan.num_parts == 0) return VB_OK;
@@ -892,6 +893,18 @@ static int radix_pass(vb_shuf *s, const Loader &ld, const Digit &dg, u64 n, KeyT
             a.keys = ld.keys; a.vals = ld.vals; a.n = n; a.n_tiles = 0;
             a.out_keys = out_keys; a.out_vals = out_vals;
             a.part_off = d_hist; a.num_parts = plan.num_parts; a.rows_per_part = plan.rows_per_part;
+            if constexpr (sizeof(KeyT) == 4 && HAS_VAL) {
+                // last pass of group_by_key's sort: value-run starts recorded by the scatter itself, ids not written (rp_gsweep_kernel<CSR>)
+                static const bool no_csr = getenv("VEGA_B200_NO_CSR_FUSION") != nullptr;
+                if (csr && !no_csr && ld.mode == LD_KEY32_VAL_SOA) {
+                    const void *ck = (const void *)rp_gsweep_kernel<u32, true, LD_KEY32_VAL_SOA, true>;
+                    if (c->occ_cache.find(ck) == c->occ_cache.end()) CU(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+                    (void)occupancy(c, ck, (int)gthreads, gsm);
+                    gk = ck;
+                    a.csr = csr;
+                    if (csr_done) *csr_done = true;
+                }
+            }
             static const u32 stagger = getenv("VEGA_B200_GS_STAGGER") ? (u32)atoi(getenv("VEGA_B200_GS_STAGGER")) : 0u;
             a.stagger_ns = stagger;
             Digit dgs = dg;
@@ -1209,16 +1222,17 @@ static int multisplit(vb_shuf *s, const Loader &ld, u64 n, int mode, u32 nbins, 
 // LSD radix sort of (u32 id, u64 val) pairs over `bits` low bits.  ids_a is overwritten.
 // The first pass reads values through `first` (ids come from ids_a).  Results: *out_ids, *out_vals
 // (owned by the caller afterwards).
-static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32 bits, u32 **out_ids, u64 **out_vals, const u32 *xlat = nullptr)
+static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32 bits, u32 **out_ids, u64 **out_vals, const u32 *xlat = nullptr,
+                         u64 *csr = nullptr, bool *csr_done = nullptr)
 {
     vb_ctx *c = s->ctx;
     const u32 passes = std::max<u32>(1, (bits + RP_SORT_BITS - 1) / RP_SORT_BITS);
-    auto translate_now = [&]() -> int {       // the stand-alone translation (paths whose first histogram does not go through rp_hist_kernel)
+    if (xlat) {                               // slot ids -> dense ids, in place
         KLaunch kl(s, K_MISC);
         u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8);
         translate_ids_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(ids_a, n, xlat);
-        return kl.done("translate_ids_kernel");
-    };
+        TRY(kl.done("translate_ids_kernel"));
+    }
     {
         Loader probe = first;
         probe.keys = ids_a;
@@ -1226,7 +1240,6 @@ static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32
         dgp.mode = DG_BITS;
         if (sweep_applicable<u32, true>(probe, dgp, n) && RP_SORT_BITS == 8) {
             // sweep path: ONE histogram read for all digit positions, then one look-back kernel per pass
-            if (xlat) TRY(translate_now());
             DevBuf bases(c), scratch(c), ids_b(c), vals_a(c), vals_b(c);
             TRY(bases.alloc((size_t)passes * SW_NB * 4));
             TRY(scratch.alloc((sweep_scratch_bytes<u32, true>(n))));
@@ -1269,14 +1282,15 @@ static int sort_id_pairs(vb_shuf *s, u32 *ids_a, const Loader &first, u64 n, u32
     u64 *src_vals = nullptr, *dst_vals = vals_b.as<u64>();
     for (u32 p = 0; p < passes; ++p) {
         Loader ld = first;
-        if (p == 0) { ld.keys = src_ids; ld.xlat = xlat; }
+        if (p == 0) ld.keys = src_ids;
         else ld = Loader{LD_KEY32_VAL_SOA, src_ids, src_vals, 0};
         Digit dg{};
         dg.mode = DG_BITS;
         dg.shift = RP_SORT_BITS * p;
         dg.mask = (1u << RP_SORT_BITS) - 1;
         dg.tx = TX_NONE;
-        TRY((radix_pass<u32, true>(s, ld, dg, n, dst_ids, dst_vals, hist.as<u32>(), plan)));
+        const bool last = (p + 1 == passes);
+        TRY((radix_pass<u32, true>(s, ld, dg, n, dst_ids, dst_vals, hist.as<u32>(), plan, last ? csr : nullptr, last ? csr_done : nullptr)));
         std::swap(src_ids, dst_ids);
         u64 *nv = (src_vals == nullptr) ? vals_a.as<u64>() : src_vals;
         src_vals = dst_vals;
@@ -1574,18 +1588,24 @@ static int seal_group(vb_shuf *s, const Gathered &g)
         TRY(kl.done("scatter_dense_kernel"));
     }
     cslot.reset();
-    // 4. ids[i] = dense_of_slot[slot_of_row[i]]: applied by the first sort pass's histogram kernel while it counts (Loader::xlat)
+    // 4. ids[i] = dense_of_slot[slot_of_row[i]]: first thing sort_id_pairs does (translate_ids_kernel)
     // 5. stable LSD sort of (id, value) — the reduce partition is the high part of the dense id
     Loader first = g.rows ? Loader{LD_KEY32_VAL_AOS, nullptr, g.rows, 0} : Loader{LD_KEY32_VAL_SOA, nullptr, g.vals, 0};
     u32 *sorted_ids = nullptr;
     u64 *sorted_vals = nullptr;
-    TRY(sort_id_pairs(s, ids.as<u32>(), first, n, ceil_log2_u64(std::max<u64>(D, 2)), &sorted_ids, &sorted_vals, dense.as<u32>()));
-    DevBuf sid_guard(c);
-    if (sorted_ids != ids.as<u32>()) sid_guard.p = sorted_ids;
-    // 6. CSR offsets
+    // 6. CSR offsets: recorded by the last sort pass itself when it runs as rp_gsweep_kernel<CSR> (offsets pre-set to all ones,
+    //    offsets[D] = n), otherwise from the sorted ids
     DevBuf offs(c);
     TRY(offs.alloc((D + 1) * 8));
-    {
+    CU(cudaMemsetAsync(offs.p, 0xFF, (D + 1) * 8, c->stream));
+    bool csr_done = false;
+    TRY(sort_id_pairs(s, ids.as<u32>(), first, n, ceil_log2_u64(std::max<u64>(D, 2)), &sorted_ids, &sorted_vals, dense.as<u32>(), offs.as<u64>(), &csr_done));
+    DevBuf sid_guard(c);
+    if (sorted_ids != ids.as<u32>()) sid_guard.p = sorted_ids;
+    if (csr_done) {
+        const u64 total = n;
+        CU(cudaMemcpyAsync(offs.as<u64>() + D, &total, 8, cudaMemcpyHostToDevice, c->stream));   // pageable 8-byte source: copied before the call returns
+    } else {
         KLaunch kl(s, K_MISC);
         u64 blocks = std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8);
         csr_bounds_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sorted_ids, n, offs.as<u64>(), D);

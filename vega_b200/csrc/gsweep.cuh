@@ -89,10 +89,15 @@ VB_D u32 match_digit8(u32 d)
     return peers;
 }
 
-template <typename KeyT, bool HAS_VAL, int LDM>
+// CSR = the LAST pass of group_by_key's (dense id, value) sort: the ids are not written out any more; instead every row whose
+// predecessor in the output has a different id records its output position as the start of that id's value run
+// (a.csr[id] = min(position); a.csr is pre-set to all ones).  A run that continues an id from an earlier tile reports a
+// larger position than the true start, which the atomicMin discards.  Replaces csr_bounds_kernel and 8 bytes/row of traffic.
+template <typename KeyT, bool HAS_VAL, int LDM, bool CSR = false>
 __global__ void __launch_bounds__((GsPlan<KeyT, HAS_VAL, LDM>::THREADS), (GsPlan<KeyT, HAS_VAL, LDM>::CTAS))
 rp_gsweep_kernel(SweepArgs a, Digit dg)
 {
+    static_assert(!CSR || (LDM == LD_KEY32_VAL_SOA && sizeof(KeyT) == 4 && HAS_VAL), "CSR: (u32 id, u64 value) rows");
     using P = GsPlan<KeyT, HAS_VAL, LDM>;
     constexpr int THREADS = P::THREADS, WARPS = P::WARPS, K = P::K, T = P::T;
     constexpr bool AOS = P::AOS, VAL_AOS = P::VAL_AOS;
@@ -241,11 +246,23 @@ rp_gsweep_kernel(SweepArgs a, Digit dg)
         if (FULL && VBUF) mbar_wait(&bar_v, it & 1u);
 
         // ---- 4. write-out: consecutive threads take consecutive output positions (runs of one digit are contiguous)
-        KeyT *ok = (KeyT *)a.out_keys;
+        [[maybe_unused]] KeyT *ok = (KeyT *)a.out_keys;
 #pragma unroll (P::WU)
         for (int j = 0; j < K; ++j) {
             const u32 p = tid + (u32)j * THREADS;
-            if (FULL || p < rows_here) {
+            const bool valid = FULL || p < rows_here;
+            if constexpr (CSR) {
+                const u32 src = valid ? perm[p] : 0u;
+                const u32 key = reinterpret_cast<const u32 *>(kbuf)[src];
+                const u64 val = reinterpret_cast<const u64 *>(vbuf)[src];
+                u32 prev = __shfl_up_sync(0xffffffffu, key, 1);              // output position p-1 is lane-1's row ...
+                if (lane == 0) prev = (valid && p > 0) ? reinterpret_cast<const u32 *>(kbuf)[perm[p - 1]] : ~key;   // ... or the previous warp's last
+                if (valid) {
+                    const u32 o = gbase[rp_digit<KeyT, DG_BITS>(dg, (KeyT)key)] + p;
+                    a.out_vals[o] = val;
+                    if (prev != key) atomicMin((unsigned long long *)a.csr + key, (unsigned long long)o);
+                }
+            } else if (valid) {
                 const u32 src = perm[p];
                 KeyT key;
                 u64 val = 0;

@@ -598,8 +598,6 @@ struct Loader {
     const void *keys;   // u64* / u32* / rows (AoS) / table keys
     const void *vals;   // u64* (table modes: the accs array) or AoS rows for LD_KEY32_VAL_AOS
     u64 cap;            // table modes: number of regular slots (row `cap` is the special slot)
-    const u32 *xlat;    // LD_KEY32_* in rp_hist_kernel only: ids[i] = xlat[ids[i]] is applied (and stored back) while counting —
-                        // group_by_key's slot -> dense-id translation rides on the first pass's histogram read (NULL: none)
 };
 
 // Loader / digit modes are compile-time (LDM, DGM): a run-time switch per item left ptxas with a
@@ -737,7 +735,23 @@ rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ 
     };
     constexpr int HB = 8;   // items per batch: keeps the u64 instantiation at <= 64 registers
     u32 tiles_since_fold = 0;
+    constexpr bool STREAM = (LDM == LD_SOA64 || LDM == LD_AOS64 || LDM == LD_KEY32_VAL_SOA || LDM == LD_KEY32_VAL_AOS);   // every row valid
     for (u64 t0 = begin + (u64)sub * RP_TILE; t0 < end; t0 += (u64)split * RP_TILE) {
+        if (STREAM && t0 + RP_TILE <= end) {      // whole tile in range: no bounds checks, no branch around the counter update
+#pragma unroll 1
+            for (int h = 0; h < RP_ITEMS; h += HB) {
+                KeyT key[HB];
+#pragma unroll
+                for (int i = 0; i < HB; ++i) {
+                    const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)(h + i) * 32 + lane;
+                    rp_load_key<KeyT, LDM>(ld, idx, key[i], pol);
+                }
+#pragma unroll
+                for (int i = 0; i < HB; ++i) pc[rp_digit<KeyT, DGM>(dg, key[i]) * 32 + lane] += 1;
+            }
+            if (++tiles_since_fold == 255 / RP_ITEMS) { fold(); tiles_since_fold = 0; }
+            continue;
+        }
 #pragma unroll 1
         for (int h = 0; h < RP_ITEMS; h += HB) {
             KeyT key[HB];
@@ -747,17 +761,6 @@ rp_hist_kernel(Loader ld, Digit dg, u64 n, u64 rows_per_part, u32 *__restrict__ 
                 const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)(h + i) * 32 + lane;
                 key[i] = 0;
                 ok[i] = (idx < end) && rp_load_key<KeyT, LDM>(ld, idx, key[i], pol);
-            }
-            if constexpr (LDM == LD_KEY32_VAL_SOA || LDM == LD_KEY32_VAL_AOS) {
-                if (ld.xlat) {      // all HB ids are loaded before the first look-up, all look-ups issued before the first store
-#pragma unroll
-                    for (int i = 0; i < HB; ++i) if (ok[i]) key[i] = (KeyT)__ldg(ld.xlat + (u32)key[i]);
-#pragma unroll
-                    for (int i = 0; i < HB; ++i) {
-                        const u64 idx = t0 + (u64)warp * (32 * RP_ITEMS) + (u64)(h + i) * 32 + lane;
-                        if (ok[i]) const_cast<u32 *>((const u32 *)ld.keys)[idx] = (u32)key[i];
-                    }
-                }
             }
 #pragma unroll
             for (int i = 0; i < HB; ++i) {
@@ -1136,6 +1139,10 @@ __global__ void scatter_dense_kernel(const u64 *__restrict__ cslot, u32 n, u32 *
 // ids[i] = dense_of_slot[ids[i]] in place (the 4 MB–64 MB dense_of_slot array is L2-resident)
 __global__ void translate_ids_kernel(u32 *__restrict__ ids, u64 n, const u32 *__restrict__ dense_of_slot)
 {
+    // One look-up per thread and iteration, 2048 threads per SM: 4.4 ms for 1e9 ids, against a floor of 3.5 ms (one L2 request per
+    // id at the 2.87e11/s the chip sustains).  Tried and slower (profiles/r2_group_glue_tried.txt): fusing the look-up into the first
+    // sort pass's histogram kernel (8.5 ms instead of 4.4 + 1.3: 24 warps per SM cannot cover two dependent L2 round trips per
+    // batch), and four ids per thread with evict-first look-ups (6.1 ms: the hint ages the table out of L2).
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (; i < n; i += stride) ids[i] = dense_of_slot[ids[i]];

@@ -75,6 +75,7 @@ struct SweepArgs {
     u32 num_parts;
     u64 rows_per_part;        // multiple of the tile size
     u32 stagger_ns;           // rp_gsweep_kernel: start delay of the second half of the grid (timing experiments)
+    u64 *csr;                 // rp_gsweep_kernel<CSR>: csr[id] = min(output position of a row that starts a run of id)
 };
 
 // ---------------------------------------------------------------------------------------------
