@@ -65,6 +65,7 @@ struct GsPlan {
     static constexpr size_t total = key_bytes * (DB ? 2 : 1) + val_bytes + perm_bytes + CNT_B;
     static constexpr int WU = K <= 12 ? K : (K % 5 == 0 ? 5 : (K % 7 == 0 ? 7 : (K % 4 == 0 ? 4 : (K % 3 == 0 ? 3 : (K % 2 == 0 ? 2 : 1)))));   // write-out unroll: divides K
     static_assert(K >= 4 && T <= 65536, "tile must fit u16 positions");
+    static_assert(total + 4096 <= (size_t)(232448 - CTAS * 1024) / CTAS, "CTAS resident CTAs fit the 227 KB of an SM");
     static_assert(key_bytes % 128 == 0 && val_bytes % 128 == 0, "bulk copy destinations stay 128-byte aligned");
 };
 
