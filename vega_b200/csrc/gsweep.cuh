@@ -10,12 +10,17 @@
 //     ranking reads only the keys, the scatter phase writes one u16 per row (perm[output position] = source row), and
 //     the write-out gathers key and value through perm and recomputes the digit from the key (a shift and a mask) —
 //     no staged copy of the values, no staged digit bytes, 27 % fewer shared-memory wavefronts per row;
-//   * no row lives in registers across a barrier (only digit|rank words), so the tile is 2-3x deeper per thread
-//     (14-20 rows) and TWO 512-thread CTAs fit on an SM: while one is issue-bound in its ranking phase the other is
-//     gathering/writing, and the tile load of one hides behind the work of the other;
-//   * the ranking is the minimal ballot sequence in PTX (and/setp, vote, predicated not, and: 4 instructions per
-//     digit bit instead of the 6 the compiler emitted), the leader test is `no lower peer` instead of ffs + shfl, and
-//     the full-tile path carries no validity checks.
+//   * no row lives in registers across a barrier (only digit|rank words), so a tile is 7-11 rows deep per thread and its
+//     buffers are filled by the copy engine while the previous tile is processed: the keys of tile t+1 land in a SECOND
+//     key buffer during tile t, the value buffer is refilled right after tile t's write-out and has the whole
+//     ranking/scan/scatter of tile t+1 to arrive.  (The first version had one tile buffer and two 512-thread CTAs per SM to
+//     hide the load behind each other: 41 % of its stall samples sat on the mbarrier wait, profiles/r2_ncu_gsweep_v1.txt.)
+//     Measured CTA shapes (profiles/r2_gsweep_shape_ab.jsonl): 1024 threads x 1 CTA per SM for rows with a value (11264-row
+//     tiles of (u32,u64)), 512 x 2 for key-only rows;
+//   * the ranking is the minimal ballot sequence in PTX (R2P, 8 x VOTE, predicated NOT, 3-input LOP3: 25 instructions
+//     per row instead of the 48 the compiler emitted for the C loop), the leader test is `no lower peer` instead of
+//     ffs + shfl, the digit bases are folded into the warp counters by the column scan, and the full-tile path carries
+//     no validity checks: 2.3 warp instructions per row (rp_sweep_kernel<STATIC>: 4.0).
 //
 // Stable: output order inside a digit = (part, tile, warp, item, lane) = input order, exactly as rp_sweep_kernel.
 // Offsets from the per-part histogram (rp_hist_kernel + rp_scan_kernel), one contiguous part per CTA; DG_BITS digits only.
